@@ -1,0 +1,147 @@
+"""Pins the oracle (oracle/oracle.c + NumPy restatements) to the reference.
+
+Every check here is against vectors the REFERENCE produced (tests/golden/*.npz, made by
+tests/golden/make_golden.py running /root/reference) or against the reference's own
+known-answer tables copied as data into those fixtures.  Where oracle/_ref (the compiled
+reference ufunc.c) is present, the oracle is additionally compared with it live.
+CPU only."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.golden.cases import RANDOM_TIE_CASES, random_tie_case, sha
+
+UMAX = np.iinfo(np.uint64).max
+
+
+def test_popcount_kat(kat_hamming):
+    # reference test/test_hamming.py:7-18
+    for i in range(int(kat_hamming["num_bit_cases"])):
+        bits = kat_hamming[f"bits_{i}"]
+        want = kat_hamming[f"bits_expected_{i}"]
+        got = np.array([oracle.lib().orc_popcount64(int(b)) for b in bits], dtype=np.uint64)
+        assert np.array_equal(got, np.broadcast_to(want, got.shape))
+        assert np.array_equal(np.bitwise_count(bits).astype(np.uint64), got)
+
+
+def test_hamming_kat(kat_hamming):
+    # reference test/test_hamming.py:22-39
+    for i in range(int(kat_hamming["num_hamming_cases"])):
+        h, q, want = kat_hamming[f"hashes_{i}"], kat_hamming[f"query_{i}"], kat_hamming[f"expected_{i}"]
+        assert np.array_equal(oracle.hamming(h, q), want)
+        assert np.array_equal(oracle.hamming_swar(h, q), want)
+        assert np.array_equal(oracle.hamming_np(h, q), want)
+
+
+def test_top10_kat_queue_matches_reference_output_exactly(kat_top10):
+    # reference test/test_hamming_top_n.py:30-173 — all 24 cases, incl. #13/#23 that depend on
+    # the eviction order.  The queue restatement must reproduce the reference's returned ARRAY
+    # (slot order), not merely the set.
+    for i in range(int(kat_top10["num_cases"])):
+        h, q = kat_top10[f"hashes_{i}"], kat_top10[f"query_{i}"]
+        rows, scores = oracle.top_k_queue(h, q, 10)
+        assert np.array_equal(rows, kat_top10[f"ref_top10_{i}"]), i
+        assert set(rows.tolist()) == set(kat_top10[f"expected_{i}"].tolist()), i
+        d = kat_top10[f"ref_dist_{i}"]
+        assert np.array_equal(oracle.hamming(h, q), d), i
+        filled = rows != UMAX
+        assert np.array_equal(scores[filled], d[rows[filled].astype(np.int64)])
+        if f"ref_cand_{i}" in kat_top10:
+            rows1000, _ = oracle.top_k_queue(h, q, 1000)
+            assert np.array_equal(rows1000, kat_top10[f"ref_cand_{i}"]), i
+
+
+def test_top10_kat_canonical_is_tie_aware_equal(kat_top10):
+    # The canonical (distance, row) rule satisfies 22/24 KATs verbatim and all 24 under the
+    # tie-aware comparator.
+    verbatim = 0
+    for i in range(int(kat_top10["num_cases"])):
+        h, q = kat_top10[f"hashes_{i}"], kat_top10[f"query_{i}"]
+        d = kat_top10[f"ref_dist_{i}"]
+        rows, dists = oracle.top_k_canonical(h, q, 10)
+        rows_np, dists_np = oracle.top_k_canonical_np(h, q, 10)
+        assert np.array_equal(rows, rows_np) and np.array_equal(dists, dists_np), i
+        assert oracle.tie_aware_equal(d, rows, kat_top10[f"ref_top10_{i}"], 10), i
+        verbatim += set(rows.tolist()) == set(kat_top10[f"expected_{i}"].tolist())
+    assert verbatim == 22
+
+
+def test_random_tie_cases_queue_and_distances(random_ties):
+    for ci, (n, w, bits_kept, seed) in enumerate(RANDOM_TIE_CASES):
+        h, q = random_tie_case(n, w, bits_kept, seed)
+        assert str(random_ties[f"in_sha_{ci}"]) == sha(h) + sha(q), "RNG drifted: regenerate goldens"
+        d = random_ties[f"ref_dist_{ci}"].astype(np.uint64)
+        assert np.array_equal(oracle.hamming(h, q), d)
+        assert np.array_equal(oracle.hamming_np(h, q), d)
+        assert np.array_equal(oracle.top_k_queue(h, q, 10)[0], random_ties[f"ref_top10_{ci}"]), ci
+        assert np.array_equal(oracle.top_k_queue(h, q, 1000)[0], random_ties[f"ref_cand_{ci}"]), ci
+        for k in (1, 10, 100, 1000):
+            rows, dists = oracle.top_k_canonical(h, q, k)
+            rows_np, dists_np = oracle.top_k_canonical_np(h, q, k)
+            assert np.array_equal(rows, rows_np) and np.array_equal(dists, dists_np)
+        assert oracle.tie_aware_equal(d, oracle.top_k_canonical(h, q, 10)[0], random_ties[f"ref_top10_{ci}"], 10)
+        assert oracle.tie_aware_equal(d, oracle.top_k_canonical(h, q, 1000)[0], random_ties[f"ref_cand_{ci}"], 1000)
+
+
+def test_c1_hash_bits_equal_reference(c1_glove):
+    # BASELINE config C1: lsh.index(glove_sample, create_projections(640, 300)) with seed 0.
+    np.random.seed(0)
+    W = oracle.create_projections(640, 300)
+    assert sha(W) == str(c1_glove["W_sha"]), "np.random legacy stream changed"
+    assert np.array_equal(W[0, :8], c1_glove["W_first"])
+    X, H = c1_glove["X"], c1_glove["H"]
+    assert np.array_equal(oracle.index(X, W), H)
+    assert np.array_equal(oracle.index_np(X, W), H)
+    dots = oracle.project(X[:7], W)
+    assert np.array_equal(np.packbits(dots >= 0, axis=-1, bitorder="little").view(np.uint64), H[:7])
+    with pytest.raises(ValueError):
+        oracle.index(X[:2], W[:100])
+
+
+def test_c1_top10_equals_reference(c1_glove):
+    H = c1_glove["H"]
+    ref = c1_glove["ref_top10"]
+    differs_from_canonical = 0
+    for i in range(len(H)):
+        rows, _ = oracle.top_k_queue(H, H[i], 10)
+        assert np.array_equal(rows, ref[i]), i
+        can, _ = oracle.top_k_canonical(H, H[i], 10)
+        differs_from_canonical += set(can.tolist()) != set(ref[i].tolist())
+    # SURVEY.md §0.4 [probe]: 238/1019 self-queries differ from the lowest-index rule
+    assert differs_from_canonical == 238
+    for j, qi in enumerate(c1_glove["q_ids"]):
+        assert np.array_equal(oracle.hamming(H, H[qi]), c1_glove["ref_dist"][j])
+        assert np.array_equal(oracle.top_k_queue(H, H[qi], 1000)[0], c1_glove["ref_cand"][j])
+        assert np.array_equal(oracle.top_k_queue(H, H[qi], 10)[0], c1_glove["ref_query"][j])
+        assert np.array_equal(np.sort(oracle.hamming(H, H[qi]))[:10], c1_glove["ref_argsort_dists"][j])
+        assert np.array_equal(oracle.two_phase(H, H[qi], 2), c1_glove["ref_two_phase"][j])
+
+
+def test_edge_cases():
+    q = np.array([3, 5], dtype=np.uint64)
+    empty = np.zeros((0, 2), dtype=np.uint64)
+    assert np.all(oracle.top_k_queue(empty, q, 10)[0] == UMAX)
+    assert np.all(oracle.top_k_canonical(empty, q, 10)[0] == UMAX)
+    one = np.array([[3, 5]], dtype=np.uint64)
+    rows, dists = oracle.top_k_canonical(one, q, 3)
+    assert rows.tolist() == [0, UMAX, UMAX] and dists.tolist() == [0, UMAX, UMAX]
+    assert oracle.num_unshared_bits(np.array([0, 7, UMAX], dtype=np.uint64), np.uint64(0)).tolist() == [0, 3, 64]
+    # SURVEY.md §8a counter-example: reference evicts row 0, keeps row 1
+    d = [5, 5, 0, 0, 0, 0, 0, 0, 0, 0, 3]
+    h = np.array([[(1 << x) - 1] for x in d], dtype=np.uint64)
+    rows, _ = oracle.top_k_queue(h, np.array([0], dtype=np.uint64), 10)
+    assert set(rows.tolist()) == {10, 1, 2, 3, 4, 5, 6, 7, 8, 9}
+    rows, _ = oracle.top_k_canonical(h, np.array([0], dtype=np.uint64), 10)
+    assert rows.tolist() == [2, 3, 4, 5, 6, 7, 8, 9, 10, 0]
+
+
+@pytest.mark.skipif(oracle.ref_ufuncs("") is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_live_against_compiled_reference():
+    uf = oracle.ref_ufuncs("")
+    rng = np.random.default_rng(42)
+    for n, w in [(1, 1), (17, 3), (1000, 10), (2500, 16), (4000, 33)]:
+        h = rng.integers(0, 2**64, size=(n, w), dtype=np.uint64) & np.uint64(0x0F0F)
+        q = rng.integers(0, 2**64, size=w, dtype=np.uint64) & np.uint64(0x0F0F)
+        assert np.array_equal(uf.hamming(h, q), oracle.hamming(h, q))
+        assert np.array_equal(uf.hamming_top_10(h, q), oracle.top_k_queue(h, q, 10)[0])
+        assert np.array_equal(uf.hamming_top_cand(h, q), oracle.top_k_queue(h, q, 1000)[0])
