@@ -1,0 +1,152 @@
+/*
+ * npsims_b200.h — C ABI of libnpsims_b200.so: the B200 (sm_100a) replacement for the native
+ * hot path of softwaredoug/np-sims (np_sims/ufunc.c + the hashing loop of np_sims/lsh.py).
+ *
+ * Plain C: raw pointers, sizes and an opaque stream handle (a cudaStream_t passed as
+ * void*).  No torch, NumPy or Python types.  Every function returns 0 on success and a
+ * negative NPS_E* code on failure; nps_last_error() returns a thread-local message.
+ * The library never falls back to the CPU: without a CUDA device every compute entry
+ * point fails with NPS_ECUDA.
+ *
+ * Two levels:
+ *   A. nps_host_*  / nps_index_*  take HOST buffers, like the reference's gufunc inner loops,
+ *      and are what a maintainer binds from ufunc.c / ctypes;
+ *   B. nps_*  (device level) take DEVICE pointers and a stream; the Python host layer
+ *      (np-sims_b200/np_sims) calls these with torch tensors as the buffer carrier.
+ *
+ * Citations "ufunc.c:LINE" / "lsh.py:LINE" are relative to /root/reference/np_sims/.
+ */
+#ifndef NPSIMS_B200_H
+#define NPSIMS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define NPS_OK 0
+#define NPS_EINVAL (-1)    /* bad argument (shape, k, alignment, null pointer) */
+#define NPS_ECUDA (-2)     /* CUDA runtime error / no device */
+#define NPS_EWORKSPACE (-3) /* workspace too small */
+
+#define NPS_MAX_K 2048u        /* largest supported top-n */
+#define NPS_MAX_WORDS 1024u    /* largest signature width in 64-bit words (65536 bits) */
+#define NPS_NONE UINT64_MAX    /* padding id when fewer than k rows exist (ufunc.c:129-132) */
+
+/* top-n result order */
+#define NPS_ORDER_CANONICAL 0  /* ascending (distance, row id): "ties broken by lowest index" */
+#define NPS_ORDER_REFERENCE 1  /* the reference queue's slot order and tie survivors, bit-exact
+                                  with ufunc.c:150-195 */
+
+/* projection arithmetic of nps_project_sign_pack */
+#define NPS_PROJ_TF32X3 0      /* 3xTF32 split on tcgen05: fp32-level accuracy */
+#define NPS_PROJ_TF32 1        /* single TF32 pass: fastest, |x.w| tolerance ~1e-3 |x||w| */
+#define NPS_PROJ_FP32_SIMT 2   /* CUDA-core fp32 FMA reference kernel (validation) */
+
+int nps_version(void);
+const char *nps_last_error(void);
+/* number of CUDA devices visible, or NPS_ECUDA */
+int nps_device_count(void);
+
+/* ------------------------------------------------------------------ A. host level ------- */
+
+/* Drop-in for the bodies behind gufunc `hamming_top_10` / `hamming_top_cand`
+ * (ufunc.c:411-441 hamming_top_{10,1000}_default and :207-406 unrolled variants):
+ * hashes[num_hashes*query_len], query[query_len] and best_rows[k] are HOST pointers,
+ * C-contiguous uint64.  Result is bit-identical to the reference (slot order, UINT64_MAX
+ * padding).  Uploads the table, runs K5 + the queue replay on device 0, downloads k ids. */
+int nps_host_hamming_top_k(const uint64_t *hashes, const uint64_t *query, uint64_t num_hashes,
+                           uint64_t query_len, uint32_t k, uint64_t *best_rows);
+
+/* Drop-in for the body of gufunc `hamming` (ufunc.c:74-106): out[num_hashes] distances. */
+int nps_host_hamming(const uint64_t *hashes, const uint64_t *query, uint64_t num_hashes,
+                     uint64_t query_len, uint64_t *out);
+
+/* A signature table resident in HBM (what lsh.index returns, lsh.py:36-44), so that
+ * repeated queries do not re-upload it. */
+typedef struct nps_index nps_index_t;
+int nps_index_create(const uint64_t *host_hashes, uint64_t num_hashes, uint32_t words, int device,
+                     nps_index_t **out_index);
+void nps_index_destroy(nps_index_t *index);
+/* Batched top-n: host_queries[num_queries*words] -> host_rows[num_queries*k] (and
+ * host_dists[num_queries*k] if not NULL).  order = NPS_ORDER_*.  Copies queries H2D, runs
+ * K2+K3 (canonical) or K5+replay (reference), copies results D2H; returns when done. */
+int nps_index_query_top_n(nps_index_t *index, const uint64_t *host_queries, uint32_t num_queries,
+                          uint32_t k, int order, uint64_t *host_rows, uint64_t *host_dists);
+/* Full distances of one query against the resident table: host_out[num_hashes]. */
+int nps_index_hamming(nps_index_t *index, const uint64_t *host_query, uint64_t *host_out);
+
+/* ------------------------------------------------------------------ B. device level ----- */
+
+/* K5 — gufunc `hamming` (ufunc.c:74-106), batched: d_out[num_queries, num_hashes] of
+ * uint16/uint32/uint64 (out_bytes = 2/4/8).  d_hashes [num_hashes, words] row-major. */
+int nps_hamming(const uint64_t *d_hashes, uint64_t num_hashes, uint32_t words,
+                const uint64_t *d_queries, uint32_t num_queries, void *d_out, int out_bytes,
+                void *stream);
+
+/* K2+K3 — gufuncs `hamming_top_10` / `hamming_top_cand` (ufunc.c:444-551) generalised to any
+ * k <= NPS_MAX_K and a batch of queries, canonical order.  d_out_rows/d_out_dists
+ * [num_queries, k] uint64 (d_out_dists may be NULL); ids are row + row_base; padding NPS_NONE.
+ * d_hashes must be 16-byte aligned.  d_workspace: nps_hamming_top_n_workspace_bytes(). */
+size_t nps_hamming_top_n_workspace_bytes(uint64_t num_hashes, uint32_t words, uint32_t num_queries,
+                                         uint32_t k);
+int nps_hamming_top_n(const uint64_t *d_hashes, uint64_t num_hashes, uint32_t words,
+                      const uint64_t *d_queries, uint32_t num_queries, uint32_t k,
+                      uint64_t row_base, uint64_t *d_out_rows, uint64_t *d_out_dists,
+                      void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Same search, but returns the per-query candidate KEYS (distance << 40 | row id, ascending,
+ * NPS_NONE padded) instead of decoded ids: the unit exchanged between GPUs (all-gather) and
+ * merged by nps_top_n_merge. d_out_keys [num_queries, k]. */
+int nps_hamming_top_n_keys(const uint64_t *d_hashes, uint64_t num_hashes, uint32_t words,
+                           const uint64_t *d_queries, uint32_t num_queries, uint32_t k,
+                           uint64_t row_base, uint64_t *d_out_keys, void *d_workspace,
+                           size_t workspace_bytes, void *stream);
+
+/* K4 — merge `num_lists` candidate-key lists per query (layout [num_queries, num_lists, k] or,
+ * with list_major != 0, [num_lists, num_queries, k] as an all-gather leaves them) into the
+ * final [num_queries, k] ids/distances.  No reference equivalent (the reference is
+ * single-process); equals running the search on the concatenated table. */
+size_t nps_top_n_merge_workspace_bytes(uint32_t num_queries, uint32_t num_lists, uint32_t k);
+int nps_top_n_merge(const uint64_t *d_keys, uint32_t num_lists, uint32_t num_queries, uint32_t k,
+                    int list_major, uint64_t *d_out_rows, uint64_t *d_out_dists, void *d_workspace,
+                    size_t workspace_bytes, void *stream);
+
+/* Reference-exact order (NPS_ORDER_REFERENCE): K5 into the workspace, then the on-device
+ * replay of the reference queue (ufunc.c:150-195).  d_out_rows [num_queries, k] in slot
+ * order; d_out_scores (nullable) the slot distances. */
+size_t nps_hamming_top_n_reference_workspace_bytes(uint64_t num_hashes, uint32_t words,
+                                                   uint32_t num_queries);
+int nps_hamming_top_n_reference(const uint64_t *d_hashes, uint64_t num_hashes, uint32_t words,
+                                const uint64_t *d_queries, uint32_t num_queries, uint32_t k,
+                                uint64_t *d_out_rows, uint64_t *d_out_scores, void *d_workspace,
+                                size_t workspace_bytes, void *stream);
+
+/* gufunc `num_unshared_bits` (ufunc.c:41-66), elementwise popcount(a ^ b) -> uint8 with
+ * NumPy-style cyclic broadcasting: d_out[i] = popc(d_a[i % len_a] ^ d_b[i % len_b]), i < n.
+ * Writes the popcount (the reference's `+=` into uninitialised memory is a bug, not parity). */
+int nps_num_unshared_bits(const uint64_t *d_a, uint64_t len_a, const uint64_t *d_b, uint64_t len_b,
+                          uint64_t n, uint8_t *d_out, void *stream);
+
+/* K1a — lsh.index / lsh.index_one (lsh.py:31-44) in the reference's own arithmetic: float64
+ * dot products on the FP64 pipe, bit j of row i = (dot(projections[j], vectors[i]) >= 0),
+ * stored at word j/64, bit j%64.  d_vectors [num_vectors, dims] float32 (vectors_are_f32 != 0)
+ * or float64; d_projections [num_projections, dims] float64; num_projections % 64 == 0.
+ * d_out [num_vectors, num_projections/64] (nullable); d_dots [num_vectors, num_projections]
+ * float64 (nullable) receives the raw projections for tolerance analysis. */
+int nps_project_sign_pack_f64(const void *d_vectors, int vectors_are_f32, uint64_t num_vectors,
+                              uint32_t dims, const double *d_projections, uint32_t num_projections,
+                              uint64_t *d_out, double *d_dots, void *stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPSIMS_B200_H */

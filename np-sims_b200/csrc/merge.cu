@@ -1,0 +1,110 @@
+// merge.cu — K3 block-merge / K4 shard-merge: reduce L sorted candidate lists per query to
+// the k best.  Replaces the final state of the reference's queue (np_sims/ufunc.c:150-195)
+// and `np.argsort(...)[:n]` (np_sims/lsh.py:54).
+//
+// Keys are 64-bit  dist << 40 | global_row  (unique per row), padding = UINT64_MAX, each
+// input list ascending.  A CTA takes a group of G lists of one query into shared memory and
+// places every element directly at its output rank
+//       rank(e) = pos_in_own_list + sum_{other lists} lower_bound(list, e)
+// (keys are unique, so ranks are a permutation; pads rank >= #real keys).  No sort network,
+// no atomics; ceil(log_G L) passes.  The last pass decodes keys to (row id, distance).
+#include "common.cuh"
+#include "merge.cuh"
+
+namespace nps {
+
+__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* a, uint32_t n, uint64_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// in : [Q, lists_in, k]   out_keys: [Q, lists_out, k]  (lists_out = ceil(lists_in / G))
+// final pass (out_rows != nullptr, lists_out == 1): rows [Q,k] u64, dists [Q,k] u64 (may be null)
+__global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __restrict__ in, uint32_t lists_in,
+                                                          size_t q_stride, size_t list_stride,
+                                                          uint32_t k, uint32_t G, uint64_t* __restrict__ out_keys,
+                                                          uint64_t* __restrict__ out_rows,
+                                                          uint64_t* __restrict__ out_dists) {
+    extern __shared__ __align__(16) uint64_t skeys[];
+    const uint32_t q = blockIdx.y, grp = blockIdx.x, lists_out = gridDim.x;
+    const uint32_t g0 = grp * G;
+    const uint32_t g = (lists_in - g0) < G ? (lists_in - g0) : G;
+    const uint32_t n = g * k;
+    const uint64_t* src = in + (size_t)q * q_stride + (size_t)g0 * list_stride;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t a = i / k;
+        skeys[i] = src[(size_t)a * list_stride + (i - a * k)];
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+        const uint32_t a = e / k, i = e - a * k;
+        const uint64_t key = skeys[e];
+        uint32_t rank = i;
+        for (uint32_t b = 0; b < g && rank < k; ++b)
+            if (b != a) rank += lower_bound_u64(skeys + b * k, k, key);
+        if (rank < k) {
+            if (out_rows) {
+                const size_t o = (size_t)q * k + rank;
+                out_rows[o] = key == kNone ? kNone : (key & ((1ull << kGlobalRowBits) - 1ull));
+                if (out_dists) out_dists[o] = key == kNone ? kNone : (key >> kGlobalRowBits);
+            } else {
+                out_keys[((size_t)q * lists_out + grp) * k + rank] = key;
+            }
+        }
+    }
+}
+
+uint32_t merge_group_size(uint32_t k) {
+    uint32_t G = kMergeSmemKeys / (k ? k : 1);
+    return G < 2 ? 2 : G;
+}
+
+size_t merge_scratch_keys(uint32_t Q, uint32_t lists, uint32_t k) {
+    // ping-pong buffer for intermediate passes: the first pass shrinks lists by G
+    const uint32_t G = merge_group_size(k);
+    if (lists <= G) return 0;
+    const uint32_t l1 = (lists + G - 1) / G;
+    const uint32_t l2 = (l1 + G - 1) / G;
+    return (size_t)Q * k * ((size_t)l1 + (l1 > G ? l2 : 0));
+}
+
+cudaError_t launch_merge(const uint64_t* keys, uint32_t Q, uint32_t lists, uint32_t k, int list_major,
+                         uint64_t* scratch, uint64_t* out_rows, uint64_t* out_dists, uint64_t* out_keys,
+                         cudaStream_t stream) {
+    if (Q == 0 || k == 0) return cudaSuccess;
+    const uint32_t G = merge_group_size(k);
+    const size_t smem = (size_t)(G < lists ? G : lists) * k * sizeof(uint64_t);
+    cudaError_t e = cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(kMergeSmemKeys * 2 * sizeof(uint64_t)));
+    if (e != cudaSuccess) return e;
+    const uint64_t* cur = keys;
+    uint32_t cur_lists = lists;
+    size_t q_stride = list_major ? (size_t)k : (size_t)lists * k;
+    size_t list_stride = list_major ? (size_t)Q * k : (size_t)k;
+    uint64_t* bufA = scratch;
+    uint64_t* bufB = scratch ? scratch + (size_t)Q * k * ((lists + G - 1) / G) : nullptr;
+    int flip = 0;
+    while (cur_lists > G) {
+        const uint32_t nxt = (cur_lists + G - 1) / G;
+        uint64_t* dst = flip ? bufB : bufA;
+        merge_lists_kernel<<<dim3(nxt, Q), 256, (size_t)G * k * 8, stream>>>(cur, cur_lists, q_stride, list_stride, k,
+                                                                             G, dst, nullptr, nullptr);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        cur = dst;
+        cur_lists = nxt;
+        q_stride = (size_t)nxt * k;
+        list_stride = k;
+        flip ^= 1;
+    }
+    // last pass: decoded ids/distances, or (out_keys) the merged key list itself
+    merge_lists_kernel<<<dim3(1, Q), 256, smem, stream>>>(cur, cur_lists, q_stride, list_stride, k, G, out_keys,
+                                                          out_keys ? nullptr : out_rows, out_keys ? nullptr : out_dists);
+    return cudaGetLastError();
+}
+
+}  // namespace nps

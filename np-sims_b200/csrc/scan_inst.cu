@@ -1,0 +1,55 @@
+// scan_inst.cu — explicit instantiations of the width-specialised scan kernel.
+// Compiled four times with -DNPS_WGROUP=0..3 (8 widths each) so the builds run in parallel,
+// plus once with -DNPS_WGROUP=4 for the generic kernel and the dispatch table.
+#if NPS_WGROUP == 4
+#define NPS_SCAN_GENERIC 1
+#endif
+#include "scan.cuh"
+
+namespace nps {
+
+template <int W>
+static cudaError_t launch_scan_w(const ScanParams& p, int grid, size_t smem, cudaStream_t stream) {
+    constexpr int R = rows_per_thread(W);
+    auto kern = scan_topk_kernel<W, R>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kScanThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+#define NPS_DECL_GROUP(g) ScanLaunchFn scan_launcher_group##g(int words);
+NPS_DECL_GROUP(0) NPS_DECL_GROUP(1) NPS_DECL_GROUP(2) NPS_DECL_GROUP(3)
+
+#if NPS_WGROUP < 4
+#define NPS_CASE(w) case (NPS_WGROUP * 8 + w): return launch_scan_w<NPS_WGROUP * 8 + w>;
+#define NPS_DEFINE_GROUP_(g)                                               \
+    ScanLaunchFn scan_launcher_group##g(int words) {                       \
+        switch (words) {                                                   \
+            NPS_CASE(1) NPS_CASE(2) NPS_CASE(3) NPS_CASE(4)                \
+            NPS_CASE(5) NPS_CASE(6) NPS_CASE(7) NPS_CASE(8)                \
+            default: return nullptr;                                       \
+        }                                                                  \
+    }
+#define NPS_DEFINE_GROUP(g) NPS_DEFINE_GROUP_(g)
+NPS_DEFINE_GROUP(NPS_WGROUP)
+#else
+ScanLaunchFn scan_launcher_for_width(int words) {
+    if (words < 1 || words > 32) return nullptr;
+    switch ((words - 1) / 8) {
+        case 0: return scan_launcher_group0(words);
+        case 1: return scan_launcher_group1(words);
+        case 2: return scan_launcher_group2(words);
+        default: return scan_launcher_group3(words);
+    }
+}
+cudaError_t launch_scan_generic(const ScanParams& p, int grid, size_t smem, cudaStream_t stream) {
+    cudaError_t e =
+        cudaFuncSetAttribute(scan_topk_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    scan_topk_generic_kernel<<<grid, kScanThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+#endif
+
+}  // namespace nps

@@ -1,0 +1,98 @@
+"""Device-buffer plumbing: torch tensors carry HBM allocations and streams, nothing more."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def torch():
+    import torch as _torch
+    return _torch
+
+
+def require_cuda():
+    t = torch()
+    if not t.cuda.is_available():
+        raise RuntimeError("npsims_b200: no CUDA device available (there is no CPU fallback)")
+    return t
+
+
+def stream_ptr() -> int:
+    return torch().cuda.current_stream().cuda_stream
+
+
+class DeviceArray(np.ndarray):
+    """An ndarray that remembers the HBM copy of its contents.
+
+    `lsh.index` / `lsh.create_projections` return these so that the reference's calling
+    pattern (index once with NumPy arrays, query many times) does not re-upload the table on
+    every call.  Views and copies do not inherit the device buffer; mutating the array in
+    place after it was uploaded is not supported (call `forget_device(arr)` first).
+    """
+
+    _nps_dev = None
+
+    def __array_finalize__(self, obj):
+        self._nps_dev = None
+
+    def __reduce__(self):  # pickle / np.save as a plain array
+        return np.asarray(self).view(np.ndarray).__reduce__()
+
+
+def attach(arr: np.ndarray, dev) -> "DeviceArray":
+    out = np.asarray(arr).view(DeviceArray)
+    out._nps_dev = dev
+    return out
+
+
+def forget_device(arr) -> None:
+    if isinstance(arr, DeviceArray):
+        arr._nps_dev = None
+
+
+def is_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def u64_table(x, name: str, ndim: int | None = None):
+    """(int64 CUDA tensor sharing the uint64 bits, came_from_host: bool)."""
+    t = require_cuda()
+    if is_tensor(x):
+        if x.dtype not in (t.int64, t.uint64):
+            raise TypeError(f"{name}: expected uint64, got {x.dtype}")
+        if not x.is_cuda:
+            x = x.cuda()
+        x = x.contiguous()
+        if x.dtype == t.uint64:
+            x = x.view(t.int64)
+        if ndim is not None and x.dim() != ndim:
+            raise ValueError(f"{name}: expected {ndim} dimensions, got {x.dim()}")
+        return x, False
+    cached = getattr(x, "_nps_dev", None) if isinstance(x, DeviceArray) else None
+    arr = np.asarray(x)
+    if arr.dtype != np.uint64:
+        # NumPy's gufunc dispatch for the reference's 'LL->L' loops (ufunc.c:564-565)
+        raise TypeError(f"ufunc '{name}' not supported for the input types ({arr.dtype}); expected uint64")
+    if ndim is not None and arr.ndim != ndim:
+        raise ValueError(f"{name}: expected {ndim} dimensions, got {arr.ndim}")
+    if cached is not None:
+        return cached, True
+    arr = np.ascontiguousarray(arr)
+    dev = t.from_numpy(arr.view(np.int64)).cuda()
+    if isinstance(x, DeviceArray):
+        x._nps_dev = dev
+    return dev, True
+
+
+def to_host_u64(tensor) -> np.ndarray:
+    return tensor.cpu().numpy().view(np.uint64)
+
+
+def empty(shape, dtype, like=None):
+    t = torch()
+    return t.empty(shape, dtype=dtype, device=like.device if like is not None else "cuda")
+
+
+def ptr(tensor) -> int:
+    return tensor.data_ptr() if tensor is not None else 0

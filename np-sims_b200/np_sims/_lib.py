@@ -1,0 +1,77 @@
+"""ctypes binding of libnpsims_b200.so (C ABI: include/npsims_b200.h).
+
+There is no CPU fallback: if the library is missing this module raises at import, and if no
+CUDA device is present every compute call raises RuntimeError with the library's message.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libnpsims_b200.so")
+
+NPS_OK, NPS_EINVAL, NPS_ECUDA, NPS_EWORKSPACE = 0, -1, -2, -3
+NPS_MAX_K, NPS_MAX_WORDS = 2048, 1024
+ORDER_CANONICAL, ORDER_REFERENCE = 0, 1
+PROJ_TF32X3, PROJ_TF32, PROJ_FP32_SIMT = 0, 1, 2
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is not built. Run `python np-sims_b200/build.py` (needs nvcc); "
+        "np_sims on B200 has no CPU fallback."
+    )
+
+_lib = ctypes.CDLL(LIB_PATH)
+
+_vp, _u64, _u32, _int, _sz = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_size_t
+
+_SIGS = {
+    "nps_version": (_int, []),
+    "nps_last_error": (ctypes.c_char_p, []),
+    "nps_device_count": (_int, []),
+    "nps_host_hamming_top_k": (_int, [_vp, _vp, _u64, _u64, _u32, _vp]),
+    "nps_host_hamming": (_int, [_vp, _vp, _u64, _u64, _vp]),
+    "nps_index_create": (_int, [_vp, _u64, _u32, _int, ctypes.POINTER(_vp)]),
+    "nps_index_destroy": (None, [_vp]),
+    "nps_index_query_top_n": (_int, [_vp, _vp, _u32, _u32, _int, _vp, _vp]),
+    "nps_index_hamming": (_int, [_vp, _vp, _vp]),
+    "nps_hamming": (_int, [_vp, _u64, _u32, _vp, _u32, _vp, _int, _vp]),
+    "nps_hamming_top_n_workspace_bytes": (_sz, [_u64, _u32, _u32, _u32]),
+    "nps_hamming_top_n": (_int, [_vp, _u64, _u32, _vp, _u32, _u32, _u64, _vp, _vp, _vp, _sz, _vp]),
+    "nps_hamming_top_n_keys": (_int, [_vp, _u64, _u32, _vp, _u32, _u32, _u64, _vp, _vp, _sz, _vp]),
+    "nps_top_n_merge_workspace_bytes": (_sz, [_u32, _u32, _u32]),
+    "nps_top_n_merge": (_int, [_vp, _u32, _u32, _u32, _int, _vp, _vp, _vp, _sz, _vp]),
+    "nps_hamming_top_n_reference_workspace_bytes": (_sz, [_u64, _u32, _u32]),
+    "nps_hamming_top_n_reference": (_int, [_vp, _u64, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _sz, _vp]),
+    "nps_num_unshared_bits": (_int, [_vp, _u64, _vp, _u64, _u64, _vp, _vp]),
+    "nps_project_sign_pack_f64": (_int, [_vp, _int, _u64, _u32, _vp, _u32, _vp, _vp, _vp]),
+}
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(_lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+EXPORTS = tuple(_SIGS)
+
+
+def last_error() -> str:
+    return _lib.nps_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    """Map a C status to the exception the reference's Python surface would raise."""
+    if rc == NPS_OK:
+        return
+    msg = last_error()
+    if rc == NPS_EINVAL:
+        raise ValueError(msg)
+    raise RuntimeError(f"npsims_b200: {msg} (status {rc})")
+
+
+def call(name: str, *args):
+    check(getattr(_lib, name)(*args))
+
+
+def raw(name: str):
+    return getattr(_lib, name)

@@ -1,0 +1,188 @@
+"""`np_sims.lsh` of the reference (/root/reference/np_sims/lsh.py) on the B200: same function
+names, arguments, return conventions and error behaviour; hashing and search run as CUDA
+kernels (K1 projection+sign+pack, K2/K3 scan+top-n, K5 distances, queue replay).
+
+Line citations are to /root/reference/np_sims/lsh.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from np_sims import hamming_c, hamming_naive, hamming_top_10, hamming_top_cand, hamming_top_n
+from . import _lib
+from ._device import DeviceArray, attach, is_tensor, ptr, require_cuda, stream_ptr, to_host_u64
+
+
+def random_projection(dims):
+    """lsh.py:5-18 — a unit vector from the GLOBAL np.random state (Gaussian, normalised).
+    Kept on the host in NumPy so that seeds reproduce the reference bit for bit."""
+    projection = np.random.normal(size=dims)
+    projection /= np.linalg.norm(projection)
+    return projection
+
+
+def create_projections(num_projections=0, dims=0) -> np.ndarray:
+    """lsh.py:21-28 — float64 [num_projections, dims].  Returned as a DeviceArray so the
+    first hashing call uploads it once."""
+    projs = [random_projection(dims) for _ in range(num_projections)]
+    return attach(np.array(projs), None)
+
+
+# ------------------------------------------------------------------------------- hashing
+def _projections_device(projections):
+    t = require_cuda()
+    if is_tensor(projections):
+        p = projections
+        if p.dtype != t.float64:
+            p = p.to(t.float64)
+        return p.cuda().contiguous()
+    cached = getattr(projections, "_nps_dev", None) if isinstance(projections, DeviceArray) else None
+    if cached is not None:
+        return cached
+    arr = np.ascontiguousarray(np.asarray(projections), dtype=np.float64)
+    dev = t.from_numpy(arr).cuda()
+    if isinstance(projections, DeviceArray):
+        projections._nps_dev = dev
+    return dev
+
+
+def _vectors_device(vectors):
+    """float32 stays float32 (NumPy upcasts it inside np.dot, lsh.py:32); everything else is
+    float64 like NumPy's own promotion."""
+    t = require_cuda()
+    if is_tensor(vectors):
+        v = vectors
+        if v.dtype not in (t.float32, t.float64):
+            v = v.to(t.float64)
+        return v.cuda().contiguous()
+    arr = np.asarray(vectors)
+    arr = np.ascontiguousarray(arr, dtype=np.float32 if arr.dtype == np.float32 else np.float64)
+    return t.from_numpy(arr).cuda()
+
+
+def hash_vectors(vectors, projections, return_dots=False):
+    """Device-level hashing: vectors [N, D] -> int64 CUDA tensor [N, B/64] carrying the uint64
+    signatures (bit j = (projections[j] . x >= 0) at word j//64, bit j%64 — lsh.py:33).
+    float64 arithmetic on the GPU (K1a).  With return_dots also the [N, B] float64 projections."""
+    t = require_cuda()
+    P = _projections_device(projections)
+    X = _vectors_device(vectors)
+    if X.dim() == 1:
+        X = X.reshape(1, -1)
+    if P.dim() != 2 or X.dim() != 2 or P.shape[1] != X.shape[1]:
+        raise ValueError(f"shapes {tuple(P.shape)} and {tuple(X.shape)} not aligned")
+    if P.shape[0] % 64 != 0:
+        raise ValueError("Projections must be a multiple of 64")
+    X = X.to(P.device)
+    out = t.empty((X.shape[0], P.shape[0] // 64), dtype=t.int64, device=P.device)
+    dots = t.empty((X.shape[0], P.shape[0]), dtype=t.float64, device=P.device) if return_dots else None
+    with t.cuda.device(P.device):
+        _lib.call("nps_project_sign_pack_f64", ptr(X), int(X.dtype == t.float32), X.shape[0], X.shape[1], ptr(P),
+                  P.shape[0], ptr(out), ptr(dots), stream_ptr())
+    return (out, dots) if return_dots else out
+
+
+def index_one(query_vector, projections):
+    """lsh.py:31-33 — one vector -> uint64[B/64]."""
+    sig = hash_vectors(query_vector, projections)[0]
+    if is_tensor(query_vector):
+        return sig.view(require_cuda().uint64)
+    return to_host_u64(sig)
+
+
+def index(vectors, projections):
+    """lsh.py:36-44 — all vectors -> uint64[N, B/64] (one batched kernel instead of the
+    reference's per-row Python loop; the progress prints of :42-43 are dropped).  The NumPy
+    result keeps its HBM copy attached (DeviceArray), so queries do not re-upload it."""
+    if len(projections) % 64 != 0:
+        raise ValueError("Projections must be a multiple of 64")
+    sigs = hash_vectors(vectors, projections)
+    if is_tensor(vectors):
+        return sigs.view(require_cuda().uint64)
+    return attach(to_host_u64(sigs), sigs)
+
+
+# ------------------------------------------------------------------------------- queries
+def _check_hamming_func(hamming_func):
+    if hamming_func not in (hamming_c, hamming_naive):
+        raise TypeError("np_sims (B200): hamming_func must be np_sims.hamming_c or np_sims.hamming_naive")
+
+
+def _as_index_dtype(ids):
+    # np.argsort returns intp indices (lsh.py:54); keep that dtype for drop-in use as an index
+    return ids.view(np.int64) if isinstance(ids, np.ndarray) else ids
+
+
+def query_with_hamming_then_slow_argsort(vector, hashes, projections, hamming_func=hamming_c, n=10):
+    """lsh.py:47-56 — distances then argsort()[:n]; returns (idxs, distances).  Here the
+    selection is the stable (distance, row) order, done on the device."""
+    _check_hamming_func(hamming_func)
+    query_hash = index_one(vector, projections)
+    idxs, sims = hamming_top_n(hashes, query_hash, n=min(int(n), max(len(hashes), 1)), return_distances=True)
+    keep = min(int(n), len(hashes))
+    return _as_index_dtype(idxs[:keep]), sims[:keep]
+
+
+def query_pure_python(vector, hashes, projections, hamming_func=hamming_naive, n=10):
+    """lsh.py:59-67 — same contract as above (the reference's NumPy-only variant)."""
+    return query_with_hamming_then_slow_argsort(vector, hashes, projections, hamming_func=hamming_func, n=n)
+
+
+def query_with_hamming_top_n(vector, hashes, projections, hamming_func=hamming_c, n=10):
+    """lsh.py:70-74 — (hamming_top_10 ids, None); `n` and `hamming_func` are ignored by the
+    reference and therefore here."""
+    query_hash = index_one(vector, projections)
+    best = hamming_top_10(hashes, query_hash)
+    return best, None
+
+
+def front_hashes(hashes, front_bits=64):
+    """lsh.py:77-81 — the first front_bits//64 words of every signature, as a new table."""
+    front_len_64 = front_bits // 64
+    if is_tensor(hashes):
+        return hashes[:, 0:front_len_64].contiguous()
+    dev = getattr(hashes, "_nps_dev", None) if isinstance(hashes, DeviceArray) else None
+    front = np.asarray(hashes)[:, 0:front_len_64].copy()
+    return attach(front, dev[:, 0:front_len_64].contiguous() if dev is not None else None)
+
+
+def query_with_hamming_top_n_two_phase(vector, front_hashes, hashes, projections, hamming_func=hamming_c, n=10):
+    """lsh.py:84-91 — top-1000 on the front words, gather, top-10 on the full signature, map
+    back.  Both selections follow the reference queue order; UINT64_MAX padding ids index the
+    last row exactly as NumPy's wrap-around does in the reference (`hashes[candidates]`)."""
+    query_hash = index_one(vector, projections)
+    query_hash_front = query_hash[:front_hashes.shape[1]]
+    candidates = hamming_top_cand(front_hashes, query_hash_front)
+    gathered = _gather_rows(hashes, candidates)
+    best = hamming_top_10(gathered, query_hash)        # device tensor (gathered lives in HBM)
+    t = require_cuda()
+    if is_tensor(candidates):
+        return candidates.view(t.int64)[best.view(t.int64)].view(t.uint64), None
+    return candidates[best.view(t.int64).cpu().numpy()], None
+
+
+def _gather_rows(hashes, candidates):
+    """hashes[candidates] on the device (ids of UINT64_MAX wrap to the last row)."""
+    t = require_cuda()
+    from ._device import u64_table
+    H, _ = u64_table(hashes, "hamming_top_10", ndim=2)
+    C, _ = u64_table(candidates, "hamming_top_10")
+    return H[C.to(H.device)]   # int64 view of UINT64_MAX is -1 -> last row
+
+
+query = query_with_hamming_top_n  # Default query to fastest
+query_two_phase = query_with_hamming_top_n_two_phase
+
+
+# ------------------------------------------------------------------------------- batched API
+def query_batch(vectors, hashes, projections, n=10, return_distances=False):
+    """Not in the reference: hash a batch of query vectors (K1) and search them in one fused
+    scan (K2/K3), canonical order.  This is the throughput path the benchmark measures."""
+    sigs = hash_vectors(vectors, projections)
+    out = hamming_top_n(hashes, sigs, n=n, return_distances=return_distances)
+    if is_tensor(vectors) or is_tensor(hashes):
+        return out
+
+    def host(x):
+        return x.cpu().numpy().view(np.uint64) if is_tensor(x) else x
+    return tuple(host(o) for o in out) if return_distances else host(out)

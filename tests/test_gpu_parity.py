@@ -1,0 +1,339 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every check compares the CUDA path
+(through the np_sims drop-in surface or the C ABI) with the oracle / the reference's golden
+vectors on the same inputs.  Integer work is compared bit for bit."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.golden.cases import RANDOM_TIE_CASES, random_tie_case
+
+pytestmark = pytest.mark.gpu
+UMAX = np.iinfo(np.uint64).max
+
+
+@pytest.fixture(scope="module")
+def nps():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import np_sims
+    return np_sims
+
+
+def rand_sigs(rng, n, w, live_bits=None):
+    h = rng.integers(0, 2**64, size=(n, w), dtype=np.uint64)
+    if live_bits is not None and live_bits < 64 * w:
+        mask = np.zeros(w, dtype=np.uint64)
+        for b in rng.choice(64 * w, size=live_bits, replace=False):
+            mask[b // 64] |= np.uint64(1) << np.uint64(b % 64)
+        h &= mask
+    return h
+
+
+# ------------------------------------------------------------------------------ K5 distances
+def test_hamming_kats(nps, kat_hamming, kat_top10):
+    for i in range(int(kat_hamming["num_hamming_cases"])):
+        h, q, want = kat_hamming[f"hashes_{i}"], kat_hamming[f"query_{i}"], kat_hamming[f"expected_{i}"]
+        got = nps.hamming_c(h, q)
+        assert got.dtype == np.uint64 and np.array_equal(got, want)
+        assert np.array_equal(nps.hamming_naive(h, q), want)
+    for i in range(int(kat_top10["num_cases"])):
+        h, q = kat_top10[f"hashes_{i}"], kat_top10[f"query_{i}"]
+        assert np.array_equal(nps.hamming_c(h, q), kat_top10[f"ref_dist_{i}"]), i
+
+
+@pytest.mark.parametrize("w", [1, 2, 3, 5, 8, 10, 16, 21, 32, 33, 40, 80, 200])
+def test_hamming_random_widths(nps, w):
+    rng = np.random.default_rng(1000 + w)
+    n = 3001
+    h, q = rand_sigs(rng, n, w), rand_sigs(rng, 5, w)
+    want = oracle.hamming_np(h, q)
+    got = nps.hamming_c(h, q)
+    assert got.shape == (5, n) and np.array_equal(got, want)
+    assert np.array_equal(nps.hamming_c(h, q[2]), want[2])
+    for dt in (np.uint16, np.uint32):
+        from np_sims import ufuncs
+        assert np.array_equal(ufuncs.hamming(h, q, out_dtype=dt), want.astype(dt))
+
+
+def test_num_unshared_bits_and_bit_count(nps, kat_hamming):
+    from np_sims.hamming import bit_count64
+    for i in range(int(kat_hamming["num_bit_cases"])):
+        bits = kat_hamming[f"bits_{i}"]
+        assert np.array_equal(bit_count64(bits.copy()), np.bitwise_count(bits).astype(np.uint64))
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 2**64, size=(7, 33), dtype=np.uint64)
+    b = rng.integers(0, 2**64, size=33, dtype=np.uint64)
+    got = nps.num_unshared_bits(a, b)
+    assert got.dtype == np.uint8 and np.array_equal(got, oracle.num_unshared_bits(a, b))
+    assert np.array_equal(nps.num_unshared_bits(a, np.uint64(0)), np.bitwise_count(a))
+
+
+# ------------------------------------------------------------------------------ reference order
+def test_top10_kats_bit_identical_to_reference(nps, kat_top10):
+    # the reference's own test (test/test_hamming_top_n.py:169-173) and more: identical ARRAY
+    for i in range(int(kat_top10["num_cases"])):
+        h, q = kat_top10[f"hashes_{i}"], kat_top10[f"query_{i}"]
+        got = nps.hamming_top_10(h, q)
+        assert got.dtype == np.uint64 and got.shape == (10,)
+        assert set(got.tolist()) == set(kat_top10[f"expected_{i}"].tolist()), i
+        assert np.array_equal(got, kat_top10[f"ref_top10_{i}"]), i
+        if f"ref_cand_{i}" in kat_top10:
+            assert np.array_equal(nps.hamming_top_cand(h, q), kat_top10[f"ref_cand_{i}"]), i
+
+
+def test_random_ties_bit_identical_to_reference(nps, random_ties):
+    for ci, (n, w, bits_kept, seed) in enumerate(RANDOM_TIE_CASES):
+        h, q = random_tie_case(n, w, bits_kept, seed)
+        assert np.array_equal(nps.hamming_top_10(h, q), random_ties[f"ref_top10_{ci}"]), ci
+        assert np.array_equal(nps.hamming_top_cand(h, q), random_ties[f"ref_cand_{ci}"]), ci
+
+
+def test_c1_glove_top10_all_queries(nps, c1_glove):
+    # BASELINE config C1: 1019 self-queries, k=10, batched through the reference-order path
+    H = c1_glove["H"]
+    got = nps.hamming_top_n(H, H, 10, order="reference")
+    assert np.array_equal(got, c1_glove["ref_top10"])
+    for j, qi in enumerate(c1_glove["q_ids"]):
+        assert np.array_equal(nps.hamming_top_cand(H, H[qi]), c1_glove["ref_cand"][j])
+        assert np.array_equal(nps.hamming_c(H, H[qi]), c1_glove["ref_dist"][j])
+    # canonical order: exact vs the stable-argsort oracle, tie-aware vs the reference
+    can, dist = nps.hamming_top_n(H, H, 10, return_distances=True)
+    for i in range(len(H)):
+        rows, d = oracle.top_k_canonical(H, H[i], 10)
+        assert np.array_equal(can[i], rows) and np.array_equal(dist[i], d), i
+        assert oracle.tie_aware_equal(oracle.hamming(H, H[i]), can[i], c1_glove["ref_top10"][i], 10)
+
+
+# ------------------------------------------------------------------------------ canonical order
+@pytest.mark.parametrize("w", list(range(1, 35)) + [40, 42, 80])
+def test_top_n_canonical_all_widths(nps, w):
+    rng = np.random.default_rng(w)
+    n = int(rng.integers(2000, 9000))
+    h = rand_sigs(rng, n, w, live_bits=min(64 * w, 24))       # heavy ties
+    q = np.concatenate([h[rng.integers(0, n, size=3)], rand_sigs(rng, 2, w, 24)])
+    for k in (1, 10, 100):
+        rows, dists = nps.hamming_top_n(h, q, k, return_distances=True)
+        assert rows.shape == (5, k) and rows.dtype == np.uint64
+        for i in range(len(q)):
+            want_r, want_d = oracle.top_k_canonical(h, q[i], k)
+            assert np.array_equal(rows[i], want_r), (w, k, i)
+            assert np.array_equal(dists[i], want_d), (w, k, i)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 9, 10, 11, 255, 256, 257, 1023, 1025, 4097, 70001])
+@pytest.mark.parametrize("w", [1, 3, 10, 16])
+def test_top_n_ragged_row_counts(nps, n, w):
+    rng = np.random.default_rng(n * 31 + w)
+    h = rand_sigs(rng, n, w, live_bits=20)
+    q = rand_sigs(rng, 1, w, live_bits=20)[0]
+    for k in (10, 1000):
+        rows, dists = nps.hamming_top_n(h, q, k, return_distances=True)
+        want_r, want_d = oracle.top_k_canonical(h, q, k)
+        assert np.array_equal(rows, want_r) and np.array_equal(dists, want_d)
+    assert np.array_equal(nps.hamming_top_10(h, q), oracle.top_k_queue(h, q, 10)[0])
+    assert np.array_equal(nps.hamming_top_cand(h, q), oracle.top_k_queue(h, q, 1000)[0])
+
+
+@pytest.mark.parametrize("nq", [1, 2, 3, 7, 129, 300])
+def test_top_n_query_batches(nps, nq):
+    rng = np.random.default_rng(nq)
+    h = rand_sigs(rng, 20011, 10)
+    q = rand_sigs(rng, nq, 10)
+    rows = nps.hamming_top_n(h, q, 10)
+    check = range(nq) if nq <= 7 else rng.choice(nq, size=12, replace=False)
+    for i in check:
+        assert np.array_equal(rows[i], oracle.top_k_canonical(h, q[i], 10)[0]), i
+
+
+def test_top_n_adversarial_orders(nps):
+    # distances strictly decreasing with the row index: every row beats the running threshold
+    n, w = 6000, 2
+    h = np.zeros((n, w), dtype=np.uint64)
+    for i in range(n):
+        bits = 127 - (i * 128) // n
+        h[i, 0] = (1 << min(bits, 64)) - 1 if bits < 64 else UMAX
+        h[i, 1] = (1 << (bits - 64)) - 1 if bits > 64 else 0
+    q = np.zeros(w, dtype=np.uint64)
+    for k in (10, 1000):
+        rows, dists = nps.hamming_top_n(h, q, k, return_distances=True)
+        want_r, want_d = oracle.top_k_canonical(h, q, k)
+        assert np.array_equal(rows, want_r) and np.array_equal(dists, want_d)
+    assert np.array_equal(nps.hamming_top_10(h, q), oracle.top_k_queue(h, q, 10)[0])
+    assert np.array_equal(nps.hamming_top_cand(h, q), oracle.top_k_queue(h, q, 1000)[0])
+    # all rows identical: pure index tie-break
+    h[:] = 7
+    assert nps.hamming_top_n(h, q, 10).tolist() == list(range(10))
+    assert np.array_equal(nps.hamming_top_10(h, q), oracle.top_k_queue(h, q, 10)[0])
+
+
+def test_sharded_search_equals_single_shot(nps):
+    # row-sharded search + key merge (the multi-GPU data path, here on one device)
+    import torch
+    from np_sims import _lib
+    rng = np.random.default_rng(77)
+    n, w, nq, k, G = 50_003, 16, 9, 100, 4
+    h = rand_sigs(rng, n, w, live_bits=40)
+    q = rand_sigs(rng, nq, w, live_bits=40)
+    single_r, single_d = nps.hamming_top_n(h, q, k, return_distances=True)
+    H = torch.from_numpy(h.view(np.int64)).cuda()
+    Q = torch.from_numpy(q.view(np.int64)).cuda()
+    bounds = [n * g // G for g in range(G + 1)]
+    keys = torch.empty((G, nq, k), dtype=torch.int64, device="cuda")
+    for g in range(G):
+        shard = H[bounds[g]:bounds[g + 1]].contiguous()
+        ws_bytes = _lib.raw("nps_hamming_top_n_workspace_bytes")(shard.shape[0], w, nq, k)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+        _lib.call("nps_hamming_top_n_keys", shard.data_ptr(), shard.shape[0], w, Q.data_ptr(), nq, k, bounds[g],
+                  keys[g].data_ptr(), ws.data_ptr(), ws_bytes, 0)
+    rows = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    dists = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    mws_bytes = _lib.raw("nps_top_n_merge_workspace_bytes")(nq, G, k)
+    mws = torch.empty(max(mws_bytes, 16), dtype=torch.uint8, device="cuda")
+    _lib.call("nps_top_n_merge", keys.data_ptr(), G, nq, k, 1, rows.data_ptr(), dists.data_ptr(), mws.data_ptr(),
+              mws_bytes, 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(rows.cpu().numpy().view(np.uint64), single_r)
+    assert np.array_equal(dists.cpu().numpy().view(np.uint64), single_d)
+
+
+# ------------------------------------------------------------------------------ K1 hashing
+def test_c1_hash_bits_equal_reference(nps, c1_glove):
+    import np_sims.lsh as lsh
+    np.random.seed(0)
+    W = lsh.create_projections(640, 300)
+    X, H = c1_glove["X"], c1_glove["H"]
+    got = lsh.index(X, W)
+    assert got.dtype == np.uint64 and got.shape == H.shape
+    flipped = int(np.bitwise_count(np.asarray(got) ^ H).sum())
+    assert flipped == 0, f"{flipped} of {H.size * 64} hash bits differ from the reference"
+    assert np.array_equal(lsh.index_one(X[774], W), H[774])
+    # lsh.query end to end == the reference's returned arrays (np_sims/lsh.py:70-74)
+    for j, qi in enumerate(c1_glove["q_ids"]):
+        ids, none = lsh.query(X[qi], got, W)
+        assert none is None and np.array_equal(ids, c1_glove["ref_query"][j])
+        idxs, sims = lsh.query_with_hamming_then_slow_argsort(X[qi], got, W, n=10)
+        assert np.array_equal(sims, c1_glove["ref_argsort_dists"][j])
+        assert np.array_equal(idxs, oracle.top_k_canonical(H, H[qi], 10)[0].astype(np.int64))
+        front = lsh.front_hashes(got, 128)
+        two, _ = lsh.query_two_phase(X[qi], front, got, W)
+        assert np.array_equal(two, c1_glove["ref_two_phase"][j])
+
+
+@pytest.mark.parametrize("dims,bits,dtype", [(50, 64, np.float64), (300, 640, np.float32), (768, 1024, np.float32),
+                                             (13, 128, np.float32)])
+def test_hash_random_vs_oracle(nps, dims, bits, dtype):
+    import np_sims.lsh as lsh
+    rng = np.random.default_rng(dims)
+    X = rng.standard_normal((777, dims)).astype(dtype)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    np.random.seed(3)
+    W = lsh.create_projections(bits, dims)
+    want = oracle.index(X, np.asarray(W))
+    got = np.asarray(lsh.index(X, W))
+    diff = np.bitwise_count(got ^ want).sum()
+    if diff:   # only summation-order noise is allowed: |x.w| at the 1e-15 level
+        dots = oracle.project(X, np.asarray(W))
+        bad = np.unpackbits((got ^ want).view(np.uint8), axis=1, bitorder="little").astype(bool)
+        assert np.abs(dots[bad]).max() < 1e-14
+    with pytest.raises(ValueError, match="multiple of 64"):
+        lsh.index(X, np.asarray(W)[:-1])
+
+
+@pytest.mark.parametrize("seed", [0, 1000])
+@pytest.mark.parametrize("num_projections", [64, 128, 256, 2560])
+@pytest.mark.parametrize("num_dims", [50, 100, 300])
+@pytest.mark.parametrize("num_fronts", [None, 64, 256])
+def test_index_and_query_gets_more_similar(nps, seed, num_projections, num_dims, num_fronts):
+    # mirrors reference test/test_lsh.py:45-73 (including its skip condition)
+    import np_sims.lsh as lsh
+    if num_fronts is not None and num_fronts <= num_projections:
+        pytest.skip("Skipping illegal state (we should test another place")
+    np.random.seed(seed)
+    projections = lsh.create_projections(num_projections, dims=num_dims)
+    query = np.zeros(num_dims)
+    query[0], query[1] = 0.8, 0.2
+    query /= np.linalg.norm(query)
+    all_vectors, similar, different = [], [], []
+    for _ in range(100):
+        alike, diff = np.zeros(num_dims), np.zeros(num_dims)
+        alike[0], diff[-1] = 1.0, 1.0
+        similar.append(len(all_vectors)); all_vectors.append(alike)
+        different.append(len(all_vectors)); all_vectors.append(diff)
+    hashed = lsh.index(np.array(all_vectors), projections)
+    if num_fronts is None:
+        results, _ = lsh.query(query, hashed, projections)
+    else:
+        results, _ = lsh.query_two_phase(query, lsh.front_hashes(hashed, num_fronts), hashed, projections)
+    for r in results:
+        assert r in similar and r not in different
+    # and the whole thing equals the oracle's restatement of the same pipeline
+    H = oracle.index(np.array(all_vectors), np.asarray(projections))
+    assert np.array_equal(np.asarray(hashed), H)
+
+
+# ------------------------------------------------------------------------------ C ABI, host level
+def test_c_abi_host_entry_points(nps, kat_top10):
+    from np_sims import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib.nps_last_error.restype = ctypes.c_char_p
+    vp = ctypes.c_void_p
+    for i in (0, 7, 13, 14, 20, 22):
+        h = np.ascontiguousarray(kat_top10[f"hashes_{i}"])
+        q = np.ascontiguousarray(kat_top10[f"query_{i}"])
+        out = np.zeros(10, dtype=np.uint64)
+        rc = lib.nps_host_hamming_top_k(vp(h.ctypes.data), vp(q.ctypes.data), ctypes.c_uint64(h.shape[0]),
+                                        ctypes.c_uint64(h.shape[1]), ctypes.c_uint32(10), vp(out.ctypes.data))
+        assert rc == 0, lib.nps_last_error()
+        assert np.array_equal(out, kat_top10[f"ref_top10_{i}"]), i
+        d = np.zeros(h.shape[0], dtype=np.uint64)
+        rc = lib.nps_host_hamming(vp(h.ctypes.data), vp(q.ctypes.data), ctypes.c_uint64(h.shape[0]),
+                                  ctypes.c_uint64(h.shape[1]), vp(d.ctypes.data))
+        assert rc == 0 and np.array_equal(d, kat_top10[f"ref_dist_{i}"])
+    # resident index, batched queries, both orders
+    rng = np.random.default_rng(9)
+    h = rand_sigs(rng, 30_001, 10, live_bits=30)
+    q = rand_sigs(rng, 33, 10, live_bits=30)
+    ix = vp()
+    assert lib.nps_index_create(vp(h.ctypes.data), ctypes.c_uint64(len(h)), 10, 0, ctypes.byref(ix)) == 0
+    rows = np.zeros((33, 10), dtype=np.uint64)
+    dists = np.zeros((33, 10), dtype=np.uint64)
+    assert lib.nps_index_query_top_n(ix, vp(q.ctypes.data), 33, 10, 0, vp(rows.ctypes.data), vp(dists.ctypes.data)) == 0
+    for i in range(33):
+        wr, wd = oracle.top_k_canonical(h, q[i], 10)
+        assert np.array_equal(rows[i], wr) and np.array_equal(dists[i], wd)
+    assert lib.nps_index_query_top_n(ix, vp(q.ctypes.data), 33, 10, 1, vp(rows.ctypes.data), None) == 0
+    for i in range(33):
+        assert np.array_equal(rows[i], oracle.top_k_queue(h, q[i], 10)[0])
+    assert lib.nps_index_query_top_n(ix, vp(q.ctypes.data), 33, 5000, 0, vp(rows.ctypes.data), None) == -1
+    assert b"k=5000" in lib.nps_last_error()
+    lib.nps_index_destroy(ix)
+
+
+def test_error_behaviour_matches_reference(nps):
+    h = np.zeros((4, 2), dtype=np.uint64)
+    with pytest.raises(TypeError):                       # NumPy: no loop for int64 (ufunc.c:564)
+        nps.hamming_top_10(h.astype(np.int64), h[0])
+    with pytest.raises(ValueError, match="core dimension"):
+        nps.hamming_top_10(h, np.zeros(3, dtype=np.uint64))
+    with pytest.raises(ValueError):
+        nps.hamming_top_n(h, h[0], 0)
+    # non-contiguous input is honoured (the reference silently mis-reads strides)
+    rng = np.random.default_rng(3)
+    big = rand_sigs(rng, 500, 6)
+    view = big[:, ::2]
+    assert np.array_equal(nps.hamming_top_n(view, view[5], 10), oracle.top_k_canonical(view, view[5], 10)[0])
+
+
+def test_torch_tensor_inputs_stay_on_device(nps):
+    import torch
+    rng = np.random.default_rng(4)
+    h, q = rand_sigs(rng, 5000, 10), rand_sigs(rng, 4, 10)
+    H = torch.from_numpy(h.view(np.int64)).cuda()
+    Q = torch.from_numpy(q.view(np.int64)).cuda()
+    rows = nps.hamming_top_n(H, Q, 10)
+    assert rows.is_cuda and rows.dtype == torch.uint64
+    got = rows.view(torch.int64).cpu().numpy().view(np.uint64)
+    for i in range(4):
+        assert np.array_equal(got[i], oracle.top_k_canonical(h, q[i], 10)[0])
