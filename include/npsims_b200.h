@@ -53,6 +53,20 @@ const char *nps_last_error(void);
 /* number of CUDA devices visible, or NPS_ECUDA */
 int nps_device_count(void);
 
+/* Measurement aids (bench.py): with profiling on, every nps_hamming_top_n* call brackets its
+ * scan (K2) and merge (K3) launches with CUDA events on the caller's stream;
+ * nps_profile_last() waits for them and returns the two device durations in milliseconds.
+ * nps_last_scan_plan() reports how the last call was tiled. Not thread-safe; off by default. */
+typedef struct nps_scan_plan {
+    uint32_t tile_rows, tile_bytes, stages, q_tile, num_qtiles, chunk_rows, num_chunks, cap,
+        smem_bytes, grid, specialised, rows_per_thread;
+} nps_scan_plan_t;
+int nps_profile_enable(int on);
+int nps_profile_last(float *scan_ms, float *merge_ms);
+int nps_last_scan_plan(nps_scan_plan_t *out);
+/* cumulative number of CUDA kernels this library has launched in this process */
+unsigned long long nps_launch_count(void);
+
 /* ------------------------------------------------------------------ A. host level ------- */
 
 /* Drop-in for the bodies behind gufunc `hamming_top_10` / `hamming_top_cand`

@@ -16,6 +16,7 @@
 
 namespace nps {
 
+unsigned long long g_launch_count = 0;
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char* fmt, ...) {
@@ -36,6 +37,11 @@ struct DeviceInfo {
     int smem_optin = 0;
 };
 
+struct ScanPlanInfo {   // mirrors nps_scan_plan_t
+    uint32_t tile_rows, tile_bytes, stages, q_tile, num_qtiles, chunk_rows, num_chunks, cap, smem_bytes, grid,
+        specialised, rows_per_thread;
+};
+
 static int device_info(DeviceInfo* out) {
     static std::mutex mu;
     static DeviceInfo cache[64];
@@ -50,6 +56,19 @@ static int device_info(DeviceInfo* out) {
         have[dev] = true;
     }
     *out = cache[dev];
+    return NPS_OK;
+}
+
+// ---------------------------------------------------------------------------- profiling aid
+// When enabled (bench.py's roofline pass only), run_top_n brackets K2 and K3 with CUDA events
+// on the launching stream so the dominant kernel can be timed per launch, on the device.
+static bool g_profile = false;
+static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
+static ScanPlanInfo g_last_plan = {};
+
+static int profile_events() {
+    for (auto& e : g_ev)
+        if (!e) NPS_CUDA(cudaEventCreate(&e));
     return NPS_OK;
 }
 
@@ -198,6 +217,14 @@ static int run_top_n(const uint64_t* d_hashes, uint64_t N, uint32_t W, const uin
     p.row_bits = pl.row_bits;
     p.stages = pl.stages;
     p.tile_rows = pl.tile_rows;
+    g_last_plan = ScanPlanInfo{pl.tile_rows, pl.tile_bytes, pl.stages, pl.q_tile, pl.num_qtiles, pl.chunk_rows,
+                               pl.num_chunks, pl.cap, pl.smem, (uint32_t)pl.grid, pl.specialised ? 1u : 0u,
+                               pl.specialised ? (uint32_t)rows_per_thread((int)W) : 1u};
+    if (g_profile) {
+        rc = profile_events();
+        if (rc) return rc;
+        NPS_CUDA(cudaEventRecord(g_ev[0], stream));
+    }
     if (pl.specialised) {
         ScanLaunchFn fn = scan_launcher_for_width((int)W);
         if (!fn) return fail(NPS_EINVAL, "no scan kernel for words=%u", W);
@@ -205,7 +232,9 @@ static int run_top_n(const uint64_t* d_hashes, uint64_t N, uint32_t W, const uin
     } else {
         NPS_CUDA(launch_scan_generic(p, pl.grid, pl.smem, stream));
     }
+    if (g_profile) NPS_CUDA(cudaEventRecord(g_ev[1], stream));
     NPS_CUDA(launch_merge(keys, Q, pl.num_chunks, k, /*list_major=*/0, scratch, d_rows, d_dists, d_keys_out, stream));
+    if (g_profile) NPS_CUDA(cudaEventRecord(g_ev[2], stream));
     return NPS_OK;
 }
 
@@ -217,6 +246,28 @@ extern "C" {
 
 int nps_version(void) { return 100; }
 const char* nps_last_error(void) { return g_err; }
+
+int nps_profile_enable(int on) {
+    g_profile = on != 0;
+    return NPS_OK;
+}
+
+int nps_profile_last(float* scan_ms, float* merge_ms) {
+    if (!g_ev[0] || !g_ev[2]) return fail(NPS_EINVAL, "no profiled call yet");
+    NPS_CUDA(cudaEventSynchronize(g_ev[2]));
+    if (scan_ms) NPS_CUDA(cudaEventElapsedTime(scan_ms, g_ev[0], g_ev[1]));
+    if (merge_ms) NPS_CUDA(cudaEventElapsedTime(merge_ms, g_ev[1], g_ev[2]));
+    return NPS_OK;
+}
+
+int nps_last_scan_plan(nps_scan_plan_t* out) {
+    if (!out) return fail(NPS_EINVAL, "out is null");
+    static_assert(sizeof(nps_scan_plan_t) == sizeof(ScanPlanInfo), "plan struct mismatch");
+    memcpy(out, &g_last_plan, sizeof(*out));
+    return NPS_OK;
+}
+
+unsigned long long nps_launch_count(void) { return __atomic_load_n(&g_launch_count, __ATOMIC_RELAXED); }
 
 int nps_device_count(void) {
     int n = 0;

@@ -95,6 +95,10 @@ __device__ __forceinline__ void sts32_volatile(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 
+// cumulative count of kernel launches issued by this library (bench.py's gpu_launches)
+extern unsigned long long g_launch_count;
+inline void count_launch(unsigned n = 1) { __atomic_fetch_add(&g_launch_count, (unsigned long long)n, __ATOMIC_RELAXED); }
+
 __host__ __device__ constexpr int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
 
 // rows each thread keeps in registers, by signature width (64-bit words)

@@ -72,6 +72,7 @@ static cudaError_t launch_dist_t(const uint64_t* H, unsigned long long N, uint32
     unsigned long long tiles = (N + tile_rows - 1) / tile_rows;
     unsigned long long grid = tiles < (unsigned long long)sm_count * 8 ? tiles : (unsigned long long)sm_count * 8;
     kern<<<(unsigned)grid, kDistThreads, smem, stream>>>(H, N, W, Q, nq, (OutT*)out, tile_rows);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -100,6 +101,7 @@ cudaError_t launch_unshared_bits(const uint64_t* a, unsigned long long na, const
     unsigned long long blocks = (n + 255) / 256;
     if (blocks > (unsigned long long)sm_count * 16) blocks = (unsigned long long)sm_count * 16;
     unshared_bits_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, b, n, na, nb, out);
+    count_launch();
     return cudaGetLastError();
 }
 

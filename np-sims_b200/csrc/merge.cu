@@ -93,6 +93,7 @@ cudaError_t launch_merge(const uint64_t* keys, uint32_t Q, uint32_t lists, uint3
         uint64_t* dst = flip ? bufB : bufA;
         merge_lists_kernel<<<dim3(nxt, Q), 256, (size_t)G * k * 8, stream>>>(cur, cur_lists, q_stride, list_stride, k,
                                                                              G, dst, nullptr, nullptr);
+        count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         cur = dst;
@@ -104,6 +105,7 @@ cudaError_t launch_merge(const uint64_t* keys, uint32_t Q, uint32_t lists, uint3
     // last pass: decoded ids/distances, or (out_keys) the merged key list itself
     merge_lists_kernel<<<dim3(1, Q), 256, smem, stream>>>(cur, cur_lists, q_stride, list_stride, k, G, out_keys,
                                                           out_keys ? nullptr : out_rows, out_keys ? nullptr : out_dists);
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -92,6 +92,7 @@ cudaError_t launch_project_f64(const void* X, int x_is_f32, unsigned long long n
         project_f64_kernel<float><<<grid, 256, 0, stream>>>((const float*)X, n_rows, dims, W, n_proj, out, dots);
     else
         project_f64_kernel<double><<<grid, 256, 0, stream>>>((const double*)X, n_rows, dims, W, n_proj, out, dots);
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -175,6 +175,7 @@ static cudaError_t launch_t(const void* dist, unsigned long long N, uint32_t nq,
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<nq, kReplayThreads, smem, stream>>>((const DistT*)dist, N, k, out_rows, out_scores);
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -15,6 +15,7 @@ static cudaError_t launch_scan_w(const ScanParams& p, int grid, size_t smem, cud
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kScanThreads, smem, stream>>>(p);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -48,6 +49,7 @@ cudaError_t launch_scan_generic(const ScanParams& p, int grid, size_t smem, cuda
         cudaFuncSetAttribute(scan_topk_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     scan_topk_generic_kernel<<<grid, kScanThreads, smem, stream>>>(p);
+    count_launch();
     return cudaGetLastError();
 }
 #endif

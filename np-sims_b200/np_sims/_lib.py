@@ -30,6 +30,10 @@ _SIGS = {
     "nps_version": (_int, []),
     "nps_last_error": (ctypes.c_char_p, []),
     "nps_device_count": (_int, []),
+    "nps_profile_enable": (_int, [_int]),
+    "nps_profile_last": (_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+    "nps_last_scan_plan": (_int, [_vp]),
+    "nps_launch_count": (ctypes.c_ulonglong, []),
     "nps_host_hamming_top_k": (_int, [_vp, _vp, _u64, _u64, _u32, _vp]),
     "nps_host_hamming": (_int, [_vp, _vp, _u64, _u64, _vp]),
     "nps_index_create": (_int, [_vp, _u64, _u32, _int, ctypes.POINTER(_vp)]),
@@ -53,6 +57,27 @@ for _name, (_res, _args) in _SIGS.items():
     _fn.argtypes = _args
 
 EXPORTS = tuple(_SIGS)
+
+
+class ScanPlan(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "tile_rows", "tile_bytes", "stages", "q_tile", "num_qtiles", "chunk_rows", "num_chunks", "cap",
+        "smem_bytes", "grid", "specialised", "rows_per_thread")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+def last_scan_plan() -> dict:
+    plan = ScanPlan()
+    check(_lib.nps_last_scan_plan(ctypes.byref(plan)))
+    return plan.as_dict()
+
+
+def profile_last():
+    a, b = ctypes.c_float(), ctypes.c_float()
+    check(_lib.nps_profile_last(ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
 
 
 def last_error() -> str:

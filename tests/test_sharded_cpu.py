@@ -1,0 +1,91 @@
+"""world_size-2 gloo test of the multi-GPU plumbing (np_sims.sharded) on CPU.
+
+The CUDA kernels cannot run here, so the two injection points of ShardedIndex are filled with
+oracle-backed stand-ins (TEST infrastructure): what is under test is the host logic — shard
+bounds, row_base offsets, the all-gather layout handed to the merge, and that shard-then-merge
+equals the single-shot search bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _oracle_local_keys(H, Q, k, row_base):
+    out = np.full((len(Q), k), np.iinfo(np.uint64).max, dtype=np.uint64)
+    for i, q in enumerate(Q):
+        rows, dists = oracle.top_k_canonical(H, q, k)
+        ok = rows != np.iinfo(np.uint64).max
+        out[i, ok] = (dists[ok] << np.uint64(40)) | (rows[ok] + np.uint64(row_base))
+    return torch.from_numpy(out.view(np.int64))
+
+
+def _oracle_merge(gathered, k):
+    g = gathered.numpy().view(np.uint64)                       # [G, q, k]
+    merged = np.sort(np.transpose(g, (1, 0, 2)).reshape(g.shape[1], -1), axis=1)[:, :k]
+    pad = merged == np.iinfo(np.uint64).max
+    rows = np.where(pad, merged, merged & np.uint64((1 << 40) - 1))
+    dists = np.where(pad, merged, merged >> np.uint64(40))
+    return rows, dists
+
+
+def _worker(rank, world, port, n, w, k, out_dir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "np-sims_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from np_sims.sharded import ShardedIndex, shard_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(123)
+    H = rng.integers(0, 2**64, size=(n, w), dtype=np.uint64) & np.uint64(0xFFFF)
+    Q = rng.integers(0, 2**64, size=(6, w), dtype=np.uint64) & np.uint64(0xFFFF)
+    b = shard_bounds(n, world)
+    assert b[0] == 0 and b[-1] == n and all(x % 2 == 0 for x in b[:-1])
+    ix = ShardedIndex.from_global(H, rank, world, local_keys_fn=_oracle_local_keys, merge_fn=_oracle_merge)
+    assert ix.row_base == b[rank] and len(ix.hashes) == b[rank + 1] - b[rank]
+    rows, dists = ix.query(Q, k)
+    np.save(os.path.join(out_dir, f"rows_{rank}.npy"), rows)
+    np.save(os.path.join(out_dir, f"dists_{rank}.npy"), dists)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,w,k", [(1001, 3, 10), (37, 2, 100)])
+def test_two_rank_shard_merge_equals_single_shot(tmp_path, n, w, k):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), n, w, k, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(123)
+    H = rng.integers(0, 2**64, size=(n, w), dtype=np.uint64) & np.uint64(0xFFFF)
+    Q = rng.integers(0, 2**64, size=(6, w), dtype=np.uint64) & np.uint64(0xFFFF)
+    r0, r1 = np.load(tmp_path / "rows_0.npy"), np.load(tmp_path / "rows_1.npy")
+    d0, d1 = np.load(tmp_path / "dists_0.npy"), np.load(tmp_path / "dists_1.npy")
+    assert np.array_equal(r0, r1) and np.array_equal(d0, d1)      # identical on every rank
+    for i in range(len(Q)):
+        want_r, want_d = oracle.top_k_canonical(H, Q[i], k)
+        assert np.array_equal(r0[i], want_r) and np.array_equal(d0[i], want_d)
+
+
+def test_shard_bounds_cover_and_align():
+    from np_sims.sharded import shard_bounds
+    for n in (0, 1, 2, 7, 1000, 100_000_001):
+        for g in (1, 2, 4, 8):
+            b = shard_bounds(n, g)
+            assert b[0] == 0 and b[-1] == n and len(b) == g + 1
+            assert all(b[i] <= b[i + 1] for i in range(g))
+            assert all(x % 2 == 0 for x in b[:-1])
