@@ -64,6 +64,24 @@ typedef struct nps_scan_plan {
 int nps_profile_enable(int on);
 int nps_profile_last(float *scan_ms, float *merge_ms);
 int nps_last_scan_plan(nps_scan_plan_t *out);
+/* Kernel family of the top-n scan.  AUTO: batches of >= 64 queries over >= 4096 rows run on
+ * the tensor cores (tcgen05 E4M3 +-1 GEMM, exact), everything else on the XOR+POPC streaming
+ * scan.  Forcing a family is for tests and measurements; results are identical. */
+#define NPS_SCAN_AUTO 0
+#define NPS_SCAN_POPC 1
+#define NPS_SCAN_MMA 2
+int nps_set_scan_path(int path);
+int nps_last_scan_path(void);
+typedef struct nps_mma_plan {
+    uint32_t n_tile, num_qtiles, cap, growth, a_stages, smem_bytes, num_phases, last_tiles,
+        last_tiles_per_chunk, last_num_chunks, last_grid, reserved;
+} nps_mma_plan_t;
+int nps_last_mma_plan(nps_mma_plan_t *out);
+/* Tensor-core path only: number of queries whose candidate buffer overflowed during the call
+ * that used d_workspace (0 in all but adversarial inputs).  Synchronises the stream.  A caller
+ * that sees a non-zero count repeats the call with NPS_SCAN_POPC (the host-level entry points
+ * and the Python layer do this themselves). */
+int nps_top_n_overflow_count(const void *d_workspace, void *stream, uint32_t *out_count);
 /* cumulative number of CUDA kernels this library has launched in this process */
 unsigned long long nps_launch_count(void);
 

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "hamming.cuh"
 #include "merge.cuh"
+#include "mma_scan.cuh"
 #include "project.cuh"
 #include "replay.cuh"
 #include "scan.cuh"
@@ -63,6 +64,9 @@ static int device_info(DeviceInfo* out) {
 // When enabled (bench.py's roofline pass only), run_top_n brackets K2 and K3 with CUDA events
 // on the launching stream so the dominant kernel can be timed per launch, on the device.
 static bool g_profile = false;
+static int g_scan_path = NPS_SCAN_AUTO;     // nps_set_scan_path
+static int g_last_path = NPS_SCAN_POPC;     // which kernel family the last top-n call used
+static MmaPlan g_last_mma_plan = {};
 static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
 static ScanPlanInfo g_last_plan = {};
 
@@ -167,6 +171,14 @@ static int plan_scan(uint64_t N, uint32_t W, uint32_t Q, uint32_t k, int sm_coun
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// Batched queries go to the tensor cores (mma_scan.cu); few queries stay on the HBM-bound
+// XOR+POPC streaming scan (scan.cuh).  NPS_SCAN_POPC / NPS_SCAN_MMA force one family.
+static bool choose_mma(uint64_t N, uint32_t W, uint32_t Q, uint32_t k, const DeviceInfo& dev, MmaPlan* mp) {
+    if (g_scan_path == NPS_SCAN_POPC) return false;
+    if (g_scan_path == NPS_SCAN_AUTO && (Q < 64 || N < 4096)) return false;
+    return mma_plan(N, W, Q, k, dev.sm_count, dev.smem_optin, mp);
+}
+
 struct TopNWorkspace {
     size_t keys_bytes, scratch_bytes, total;
 };
@@ -190,6 +202,25 @@ static int run_top_n(const uint64_t* d_hashes, uint64_t N, uint32_t W, const uin
     DeviceInfo dev;
     int rc = device_info(&dev);
     if (rc) return rc;
+    if (W == 0 || W > NPS_MAX_WORDS) return fail(NPS_EINVAL, "words=%u outside [1, %u]", W, NPS_MAX_WORDS);
+    if (k == 0 || k > NPS_MAX_K) return fail(NPS_EINVAL, "k=%u outside [1, %u]", k, NPS_MAX_K);
+    if (Q == 0) return fail(NPS_EINVAL, "num_queries must be > 0");
+    MmaPlan mp;
+    if (choose_mma(N, W, Q, k, dev, &mp)) {
+        if (ws_bytes < mp.total || !ws) return fail(NPS_EWORKSPACE, "workspace %zu bytes < required %zu", ws_bytes, mp.total);
+        if (reinterpret_cast<uintptr_t>(ws) & 255u) return fail(NPS_EINVAL, "workspace must be 256-byte aligned");
+        g_last_path = NPS_SCAN_MMA;
+        g_last_mma_plan = mp;
+        if (g_profile) {
+            rc = profile_events();
+            if (rc) return rc;
+        }
+        NPS_CUDA(run_mma_top_n(mp, d_hashes, N, W, d_queries, Q, k, row_base, d_rows, d_dists, d_keys_out, ws, stream,
+                               g_profile ? g_ev[0] : nullptr, g_profile ? g_ev[1] : nullptr));
+        if (g_profile) NPS_CUDA(cudaEventRecord(g_ev[2], stream));
+        return NPS_OK;
+    }
+    g_last_path = NPS_SCAN_POPC;
     ScanPlan pl;
     rc = plan_scan(N, W, Q, k, dev.sm_count, dev.smem_optin, &pl);
     if (rc) return rc;
@@ -267,6 +298,30 @@ int nps_last_scan_plan(nps_scan_plan_t* out) {
     return NPS_OK;
 }
 
+int nps_set_scan_path(int path) {
+    if (path != NPS_SCAN_AUTO && path != NPS_SCAN_POPC && path != NPS_SCAN_MMA) return fail(NPS_EINVAL, "bad scan path %d", path);
+    g_scan_path = path;
+    return NPS_OK;
+}
+
+int nps_last_scan_path(void) { return g_last_path; }
+
+int nps_last_mma_plan(nps_mma_plan_t* out) {
+    if (!out) return fail(NPS_EINVAL, "out is null");
+    const MmaPlan& m = g_last_mma_plan;
+    const MmaPhase& L = m.phase[m.num_phases ? m.num_phases - 1 : 0];
+    *out = nps_mma_plan_t{m.n_tile, m.num_qtiles, m.cap, m.growth, m.a_stages, m.smem, m.num_phases,
+                          L.tiles, L.tiles_per_chunk, L.num_chunks, L.grid, 0};
+    return NPS_OK;
+}
+
+int nps_top_n_overflow_count(const void* d_workspace, void* stream, uint32_t* out_count) {
+    if (!d_workspace || !out_count) return fail(NPS_EINVAL, "null pointer");
+    NPS_CUDA(cudaMemcpyAsync(out_count, d_workspace, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    NPS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return NPS_OK;
+}
+
 unsigned long long nps_launch_count(void) { return __atomic_load_n(&g_launch_count, __ATOMIC_RELAXED); }
 
 int nps_device_count(void) {
@@ -297,6 +352,12 @@ size_t nps_hamming_top_n_workspace_bytes(uint64_t num_hashes, uint32_t words, ui
         dev.sm_count = 148;
         dev.smem_optin = 232448;
     }
+    if (words == 0 || words > NPS_MAX_WORDS || k == 0 || k > NPS_MAX_K || num_queries == 0) {
+        fail(NPS_EINVAL, "bad shape: words=%u k=%u num_queries=%u", words, k, num_queries);
+        return 0;
+    }
+    MmaPlan mp;
+    if (choose_mma(num_hashes, words, num_queries, k, dev, &mp)) return mp.total;
     ScanPlan pl;
     if (plan_scan(num_hashes, words, num_queries, k, dev.sm_count, dev.smem_optin, &pl) != NPS_OK) return 0;
     return topn_workspace(pl, num_queries, k).total;

@@ -1,0 +1,582 @@
+// mma_scan.cu — K2T kernels: tensor-core batched Hamming scan + candidate select.
+// See mma_scan.cuh for the design.  Replaces, for query batches, the scan bodies of
+// np_sims/ufunc.c:207-441 (XOR + popcount + queue insert) with an exact +-1 E4M3 GEMM.
+#include "mma_scan.cuh"
+
+namespace nps {
+
+// 4 signature bits -> 4 E4M3 bytes: bit 0 -> +1.0 (0x38), bit 1 -> -1.0 (0xB8).
+// n * 0x10204080 places bit i of the nibble at bit 8*i+7 (the copies do not overlap).
+__device__ __forceinline__ uint32_t expand4(uint32_t nib) {
+    return ((nib * 0x10204080u) & 0x80808080u) | 0x38383838u;
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Expand one 128-bit K-block (words w0, w1) of operand row `r` into its 128-byte swizzled row.
+// tile_base: shared address of the [rows x 128 B] SWIZZLE_128B tile (1024-byte aligned).
+__device__ __forceinline__ void expand_row_kblock(uint32_t tile_base, uint32_t r, uint64_t w0, uint64_t w1,
+                                                  bool have0, bool have1) {
+    const uint32_t r7 = r & 7u;
+    const uint32_t row_base = tile_base + (r >> 3) * 1024u + r7 * 128u;
+    const uint32_t half[4] = {(uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32)};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint32_t bits16 = (half[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
+        const bool have = c < 4 ? have0 : have1;
+        uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;     // E4M3 zero: contributes nothing to the dot
+        if (have) {
+            x0 = expand4(bits16 & 15u);
+            x1 = expand4((bits16 >> 4) & 15u);
+            x2 = expand4((bits16 >> 8) & 15u);
+            x3 = expand4(bits16 >> 12);
+        }
+        sts128(row_base + (((uint32_t)c ^ r7) << 4), x0, x1, x2, x3);
+    }
+}
+
+__device__ __forceinline__ uint32_t phase_tile(const MmaScanParams& p, uint32_t i) {
+    const uint32_t j = p.skip_mod ? (i + i / (p.skip_mod - 1u) + 1u) : i;
+    return j * p.tile_stride;
+}
+
+__device__ __forceinline__ void global_append(const MmaScanParams& p, uint32_t q, uint64_t key) {
+    const uint32_t pos = atomicAdd(p.cnt + q, 1u);
+    if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = key;
+}
+
+// slow path of the epilogue: exact test against the k-th best key, then stage the survivor in
+// this warp's shared-memory buffer (flushed with up to 32 global atomics in flight per warp)
+__device__ __noinline__ void record_hit(const MmaScanParams& p, uint32_t q, uint64_t key, uint32_t* wcnt,
+                                        uint64_t* hitk, uint32_t* hitq) {
+    if (key < __ldg(p.thrK + q)) {
+        const uint32_t idx = atomicAdd(wcnt, 1u);
+        if (idx < (uint32_t)kMmaHitsPerWarp) {
+            hitk[idx] = key;
+            hitq[idx] = q;
+        } else {
+            global_append(p, q, key);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const uint32_t W = p.words, KB = mma_kblocks(W), NT = p.n_tile;
+    const MmaSmem L = mma_smem_layout(W, NT, p.a_stages, p.p_stages);
+    const uint32_t AS = p.a_stages, PS = p.p_stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+    uint64_t* p_full = bars;
+    uint64_t* p_empty = p_full + PS;
+    uint64_t* a_full = p_empty + PS;
+    uint64_t* a_empty = a_full + AS;
+    uint64_t* acc_full = a_empty + AS;      // [2]
+    uint64_t* acc_empty = acc_full + 2;     // [2]
+    uint64_t* b_full = acc_empty + 2;       // [1]
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
+    uint32_t* wcnt_s = reinterpret_cast<uint32_t*>(smem + L.wcnt_off);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (uint32_t s = 0; s < PS; ++s) {
+            mbar_init(&p_full[s], 1);
+            mbar_init(&p_empty[s], kMmaTileRows);
+        }
+        for (uint32_t s = 0; s < AS; ++s) {
+            mbar_init(&a_full[s], kMmaTileRows);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], kMmaEpiWarps);
+        }
+        mbar_init(b_full, kMmaTileRows);
+        fence_mbar_init();
+    }
+    if (tid < kMmaEpiWarps) wcnt_s[tid] = 0;
+    if (warp == 1) tmem_alloc(tmem_ptr_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_s);
+
+    const uint32_t total_items = p.num_chunks * p.num_qtiles;
+    const uint32_t row_bytes = W * 8;
+
+    if (warp == 0) {
+        // =========================== producer: bit-packed row tiles ===========================
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+                const uint32_t chunk = item / p.num_qtiles;
+                const uint32_t i0 = chunk * p.tiles_per_chunk;
+                const uint32_t i1 = min(i0 + p.tiles_per_chunk, p.phase_tiles);
+                for (uint32_t i = i0; i < i1; ++i) {
+                    const unsigned long long row0 = (unsigned long long)phase_tile(p, i) * kMmaTileRows;
+                    const unsigned long long left = p.N - row0;
+                    const uint32_t rows = left < (unsigned long long)kMmaTileRows ? (uint32_t)left : kMmaTileRows;
+                    mbar_wait(&p_empty[s], ph ^ 1u);
+                    const uint32_t bytes = rows * row_bytes, bulk = bytes & ~15u;
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.hashes) + row0 * row_bytes;
+                    uint8_t* dst = smem + L.p_off + s * L.p_stride;
+                    if (bytes != bulk)
+                        *reinterpret_cast<volatile uint64_t*>(dst + bulk) =
+                            *reinterpret_cast<const uint64_t*>(src + bulk);
+                    mbar_arrive_expect_tx(&p_full[s], bulk);
+                    if (bulk) bulk_g2s(dst, src, bulk, &p_full[s]);
+                    if (++s == PS) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer =================================================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(0, 0, kMmaTileRows, NT);
+            const uint32_t ksteps_last = (W & 1u) ? 2u : 4u;
+            uint32_t as = 0, aph = 0, t_idx = 0, it_idx = 0;
+            for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x, ++it_idx) {
+                const uint32_t chunk = item / p.num_qtiles;
+                const uint32_t i0 = chunk * p.tiles_per_chunk;
+                const uint32_t i1 = min(i0 + p.tiles_per_chunk, p.phase_tiles);
+                mbar_wait(b_full, it_idx & 1u);
+                for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
+                    const uint32_t buf = t_idx & 1u;
+                    mbar_wait(&acc_empty[buf], ((t_idx >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * NT;
+                    for (uint32_t kb = 0; kb < KB; ++kb) {
+                        mbar_wait(&a_full[as], aph);
+                        tc_fence_after();
+                        const uint32_t a_addr = base + L.a_off + as * kMmaAStageBytes;
+                        const uint32_t b_addr = base + L.b_off + kb * NT * kMmaKBlockBytes;
+                        const uint32_t ks = (kb + 1 == KB) ? ksteps_last : 4u;
+                        for (uint32_t j = 0; j < ks; ++j)
+                            umma_f8(d_tmem, umma_desc_k_sw128(a_addr + j * 32u), umma_desc_k_sw128(b_addr + j * 32u),
+                                    idesc, (kb | j) != 0u);
+                        umma_commit(&a_empty[as]);     // A stage may be overwritten once these MMAs retire
+                        if (++as == AS) {
+                            as = 0;
+                            aph ^= 1u;
+                        }
+                    }
+                    umma_commit(&acc_full[buf]);       // accumulator complete -> epilogue
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // =========================== expanders: bits -> E4M3 operand tiles =======================
+        const uint32_t u = tid - 64;   // 0..127 = operand row
+        uint32_t as = 0, aph = 0, ps = 0, pph = 0, t_idx = 0;
+        for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+            const uint32_t chunk = item / p.num_qtiles, qt = item - chunk * p.num_qtiles;
+            const uint32_t q0 = qt * NT;
+            const uint32_t i0 = chunk * p.tiles_per_chunk;
+            const uint32_t i1 = min(i0 + p.tiles_per_chunk, p.phase_tiles);
+            // B (query tile) is resident for the whole item; the previous item's MMAs must have
+            // retired before it is overwritten.
+            if (t_idx > 0) mbar_wait(&acc_full[(t_idx - 1) & 1u], ((t_idx - 1) >> 1) & 1u);
+            for (uint32_t n = u; n < NT; n += kMmaTileRows) {
+                const bool valid = q0 + n < p.Q;
+                const uint64_t* src = p.queries + (size_t)(valid ? q0 + n : 0) * W;
+                for (uint32_t kb = 0; kb < KB; ++kb) {
+                    const bool h1 = 2 * kb + 1 < W;
+                    const uint64_t w0 = valid ? __ldg(src + 2 * kb) : 0ull;
+                    const uint64_t w1 = (valid && h1) ? __ldg(src + 2 * kb + 1) : 0ull;
+                    expand_row_kblock(base + L.b_off + kb * NT * kMmaKBlockBytes, n, w0, w1, valid, valid && h1);
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(b_full);
+            for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
+                const unsigned long long row0 = (unsigned long long)phase_tile(p, i) * kMmaTileRows;
+                const bool valid = row0 + u < p.N;
+                mbar_wait(&p_full[ps], pph);
+                const uint64_t* my = reinterpret_cast<const uint64_t*>(smem + L.p_off + ps * L.p_stride) + (size_t)u * W;
+                for (uint32_t kb = 0; kb < KB; ++kb) {
+                    const bool h1 = 2 * kb + 1 < W;
+                    const uint64_t w0 = valid ? my[2 * kb] : 0ull;
+                    const uint64_t w1 = (valid && h1) ? my[2 * kb + 1] : 0ull;
+                    mbar_wait(&a_empty[as], aph ^ 1u);
+                    expand_row_kblock(base + L.a_off + as * kMmaAStageBytes, u, w0, w1, valid, valid && h1);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&a_full[as]);
+                    if (++as == AS) {
+                        as = 0;
+                        aph ^= 1u;
+                    }
+                }
+                mbar_arrive(&p_empty[ps]);
+                if (++ps == PS) {
+                    ps = 0;
+                    pph ^= 1u;
+                }
+            }
+        }
+    } else {
+        // =========================== epilogue: filter + append ====================================
+        const uint32_t ew = warp - 6;                 // 0..7
+        const uint32_t quarter = warp & 3u;           // TMEM lanes this warp may read
+        const uint32_t r_in_tile = quarter * 32u + lane;
+        const uint32_t ngroups = NT / 32u;
+        const uint32_t g_split = (ngroups + 1u) / 2u;
+        const uint32_t g_begin = (ew < 4) ? 0u : g_split;
+        const uint32_t g_end = (ew < 4) ? g_split : ngroups;
+        uint64_t* hitk = reinterpret_cast<uint64_t*>(smem + L.hitk_off) + ew * kMmaHitsPerWarp;
+        uint32_t* hitq = reinterpret_cast<uint32_t*>(smem + L.hitq_off) + ew * kMmaHitsPerWarp;
+        uint32_t* wcnt = wcnt_s + ew;
+        const int bits = (int)(W * 64u);
+        uint32_t t_idx = 0;
+        for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+            const uint32_t chunk = item / p.num_qtiles, qt = item - chunk * p.num_qtiles;
+            const uint32_t q0 = qt * NT;
+            const uint32_t i0 = chunk * p.tiles_per_chunk;
+            const uint32_t i1 = min(i0 + p.tiles_per_chunk, p.phase_tiles);
+            for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
+                const uint32_t buf = t_idx & 1u;
+                const unsigned long long row = (unsigned long long)phase_tile(p, i) * kMmaTileRows + r_in_tile;
+                const bool valid = row < p.N;
+                const uint64_t grow = p.row_base + row;
+                mbar_wait(&acc_full[buf], (t_idx >> 1) & 1u);
+                tc_fence_after();
+                for (uint32_t g = g_begin; g < g_end; ++g) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((quarter * 32u) << 16) + buf * NT + g * 32u, v);
+                    const uint32_t qg = q0 + g * 32u;
+                    if (p.dense) {
+                        tmem_ld_wait();
+                        const size_t slot = (size_t)i * kMmaTileRows + r_in_tile;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (qg + j < p.Q) {
+                                const uint64_t d = (uint64_t)((bits - (int)__uint_as_float(v[j])) >> 1);
+                                p.cand[(size_t)(qg + j) * p.cap + slot] = valid ? ((d << kGlobalRowBits) | grow) : kNone;
+                            }
+                        }
+                        continue;
+                    }
+                    float T[32];
+                    const float4* tp = reinterpret_cast<const float4*>(p.thrT + qg);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t4 = __ldg(tp + j);
+                        T[4 * j + 0] = t4.x;
+                        T[4 * j + 1] = t4.y;
+                        T[4 * j + 2] = t4.z;
+                        T[4 * j + 3] = t4.w;
+                    }
+                    tmem_ld_wait();
+                    bool any = false;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) any |= __uint_as_float(v[j]) >= T[j];
+                    any = any && valid;
+                    if (__any_sync(0xffffffffu, any)) {
+                        if (any) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (__uint_as_float(v[j]) >= T[j]) {
+                                    const uint64_t d = (uint64_t)((bits - (int)__uint_as_float(v[j])) >> 1);
+                                    const uint64_t key = (d << kGlobalRowBits) | grow;
+                                    record_hit(p, qg + j, key, wcnt, hitk, hitq);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                // flush this warp's hit buffer: up to 32 global appends in flight at a time
+                if (!p.dense) {
+                    const uint32_t n = min(*reinterpret_cast<volatile uint32_t*>(wcnt), (uint32_t)kMmaHitsPerWarp);
+                    if (n) {
+                        for (uint32_t e = lane; e < n; e += 32) global_append(p, hitq[e], hitk[e]);
+                        __syncwarp();
+                        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(wcnt) = 0;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+cudaError_t launch_mma_scan(const MmaScanParams& p, int grid, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(mma_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mma_scan_kernel<<<grid, kMmaThreads, smem, stream>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// mma_select_kernel — fold a phase's candidates into the running exact top-k of every query.
+// One CTA per query: keys of (previous best ++ candidates) are bitonic-sorted in shared memory
+// (sort size = next power of two of the actual count), the k smallest become the new best,
+// and the k-th one becomes the next phase's threshold.
+// =============================================================================================
+constexpr int kSelectThreads = 128;
+
+__global__ void __launch_bounds__(kSelectThreads) mma_select_kernel(const MmaSelectParams p) {
+    extern __shared__ __align__(16) uint64_t skeys[];
+    const uint32_t q = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (q >= p.Q) {   // padding entries of the threshold arrays: never pass
+        if (tid == 0) {
+            p.thrT[q] = __int_as_float(0x7f800000);
+            p.thrK[q] = 0ull;
+        }
+        return;
+    }
+    uint32_t cnt = p.fixed_cnt >= 0 ? (uint32_t)p.fixed_cnt : p.cnt[q];
+    if (cnt > p.cap) {
+        if (tid == 0) atomicAdd(p.overflow, 1u);
+        cnt = p.cap;
+    }
+    const uint32_t nbest = p.first ? 0u : p.k;
+    const uint32_t n = nbest + cnt;
+    uint32_t S = 32;
+    while (S < n) S <<= 1;
+    for (uint32_t i = tid; i < S; i += kSelectThreads) {
+        uint64_t key = kNone;
+        if (i < nbest) key = p.best[(size_t)q * p.k + i];
+        else if (i < n) key = p.cand[(size_t)q * p.cap + (i - nbest)];
+        skeys[i] = key;
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= S; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = tid; i < (S >> 1); i += kSelectThreads) {
+                const uint32_t pos = 2 * i - (i & (stride - 1));
+                const uint64_t a = skeys[pos], b = skeys[pos + stride];
+                const bool up = (pos & size) == 0;
+                if ((a > b) == up) {
+                    skeys[pos] = b;
+                    skeys[pos + stride] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = tid; i < p.k; i += kSelectThreads) {
+        const uint64_t key = i < S ? skeys[i] : kNone;
+        p.best[(size_t)q * p.k + i] = key;
+        if (p.out_keys) p.out_keys[(size_t)q * p.k + i] = key;
+        if (p.out_rows) p.out_rows[(size_t)q * p.k + i] = key == kNone ? kNone : (key & ((1ull << kGlobalRowBits) - 1ull));
+        if (p.out_dists) p.out_dists[(size_t)q * p.k + i] = key == kNone ? kNone : (key >> kGlobalRowBits);
+    }
+    if (tid == 0) {
+        const uint64_t kth = (p.k - 1 < S) ? skeys[p.k - 1] : kNone;
+        p.thrK[q] = kth;
+        // pass iff dist <= dist_k  <=>  dot >= bits - 2 dist_k   (no k-th key yet: everything passes)
+        p.thrT[q] = kth == kNone ? __int_as_float(0xff800000)
+                                 : (float)((int)p.bits - 2 * (int)(kth >> kGlobalRowBits));
+        if (p.fixed_cnt < 0) p.cnt[q] = 0;
+    }
+}
+
+cudaError_t launch_mma_select(const MmaSelectParams& p, cudaStream_t stream) {
+    const size_t smem = (size_t)p.sort_cap * 8;
+    cudaError_t e = cudaFuncSetAttribute(mma_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mma_select_kernel<<<p.Qpad, kSelectThreads, smem, stream>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+
+// =============================================================================================
+// host: plan + phase loop
+// =============================================================================================
+static uint32_t pow2_ceil(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_count, int smem_optin, MmaPlan* pl) {
+    if (W == 0 || W > kMmaMaxWords || k == 0 || k > 1024 || Q == 0 || N == 0) return false;
+    if (N > (1ull << 38)) return false;
+    if (sm_count <= 0) sm_count = 148;
+    if (smem_optin <= 0) smem_optin = 232448;
+    // ---- operand tile: the widest query tile (multiple of 32, <= 256) that fits next to >= 2 A stages
+    const uint32_t want = ((Q < 256u ? Q : 256u) + 31u) & ~31u;
+    uint32_t n_tile = 0, a_stages = 0;
+    for (uint32_t nt = want; nt >= 32 && !n_tile; nt -= 32)
+        for (uint32_t as = 4; as >= 2; --as)
+            if (mma_smem_layout(W, nt, as, 2).total <= (uint32_t)smem_optin) {
+                n_tile = nt;
+                a_stages = as;
+                break;
+            }
+    if (!n_tile) return false;
+    pl->n_tile = n_tile;
+    pl->a_stages = a_stages;
+    pl->p_stages = 2;
+    pl->smem = mma_smem_layout(W, n_tile, a_stages, 2).total;
+    pl->num_qtiles = (Q + n_tile - 1) / n_tile;
+    pl->q_pad = pl->num_qtiles * n_tile;
+    // ---- candidate capacity and phase growth: expected survivors per phase ~ k * growth <= cap / 4
+    uint32_t cap = pow2_ceil(16u * k);
+    if (cap < 512u) cap = 512u;
+    if (cap > 8192u) cap = 8192u;
+    uint32_t growth = cap / (4u * k);
+    if (growth > 8u) growth = 8u;
+    if (growth < 2u) growth = 2u;
+    pl->cap = cap;
+    pl->growth = growth;
+    pl->sort_cap = pow2_ceil(k + cap);
+    // ---- phases: tile strides G^(P-1), ..., G, 1; the first (dense) phase must fit the buffer
+    const unsigned long long T = (N + kMmaTileRows - 1) / kMmaTileRows;
+    if (T > 0x7FFFFFFFull) return false;
+    const uint32_t tiles0_max = cap / kMmaTileRows;
+    uint32_t strides[kMmaMaxPhases];
+    uint32_t np = 1;
+    strides[0] = 1;
+    while ((T + strides[np - 1] - 1) / strides[np - 1] > tiles0_max) {
+        if (np == kMmaMaxPhases) return false;
+        const unsigned long long nxt = (unsigned long long)strides[np - 1] * growth;
+        if (nxt > 0x7FFFFFFFull) return false;
+        strides[np] = (uint32_t)nxt;
+        ++np;
+    }
+    pl->num_phases = np;
+    for (uint32_t ph = 0; ph < np; ++ph) {
+        MmaPhase& P = pl->phase[ph];
+        P.stride = strides[np - 1 - ph];
+        const uint32_t J = (uint32_t)((T + P.stride - 1) / P.stride);
+        if (ph == 0) {
+            P.skip_mod = 0;
+            P.tiles = J;
+        } else {
+            P.skip_mod = growth;
+            P.tiles = J - (J + growth - 1) / growth;
+        }
+        // chunks: balance waves of (chunk, query tile) items over the SMs; ~1.5 tiles of fixed
+        // cost per item (query-tile expansion + pipeline drain)
+        double best_cost = 1e300;
+        uint32_t best_tpc = P.tiles ? P.tiles : 1;
+        const uint32_t cmax = P.tiles < 4096u ? P.tiles : 4096u;
+        for (uint32_t c = 1; c <= cmax; ++c) {
+            const uint32_t tpc = (P.tiles + c - 1) / c;
+            const uint32_t chunks = (P.tiles + tpc - 1) / tpc;
+            const unsigned long long items = (unsigned long long)chunks * pl->num_qtiles;
+            const unsigned long long waves = (items + sm_count - 1) / sm_count;
+            const double cost = (double)waves * ((double)tpc + 1.5);
+            if (cost < best_cost) {
+                best_cost = cost;
+                best_tpc = tpc;
+            }
+        }
+        P.tiles_per_chunk = best_tpc;
+        P.num_chunks = P.tiles ? (P.tiles + best_tpc - 1) / best_tpc : 0;
+        const unsigned long long items = (unsigned long long)P.num_chunks * pl->num_qtiles;
+        P.grid = (uint32_t)(items < (unsigned long long)sm_count ? items : (unsigned long long)sm_count);
+    }
+    // ---- workspace
+    size_t off = 0;
+    pl->off_flag = off;
+    off += 256;
+    pl->off_cnt = off;
+    off += align256((size_t)Q * 4);
+    pl->off_thrT = off;
+    off += align256((size_t)pl->q_pad * 4);
+    pl->off_thrK = off;
+    off += align256((size_t)pl->q_pad * 8);
+    pl->off_best = off;
+    off += align256((size_t)Q * k * 8);
+    pl->off_cand = off;
+    off += align256((size_t)Q * cap * 8);
+    pl->total = off;
+    return true;
+}
+
+cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned long long N, uint32_t W,
+                          const uint64_t* d_queries, uint32_t Q, uint32_t k, unsigned long long row_base,
+                          uint64_t* d_rows, uint64_t* d_dists, uint64_t* d_keys, void* ws, cudaStream_t stream,
+                          cudaEvent_t ev_scan_begin, cudaEvent_t ev_scan_end) {
+    uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+    uint32_t* flag = reinterpret_cast<uint32_t*>(w8 + pl.off_flag);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(w8 + pl.off_cnt);
+    float* thrT = reinterpret_cast<float*>(w8 + pl.off_thrT);
+    uint64_t* thrK = reinterpret_cast<uint64_t*>(w8 + pl.off_thrK);
+    uint64_t* best = reinterpret_cast<uint64_t*>(w8 + pl.off_best);
+    uint64_t* cand = reinterpret_cast<uint64_t*>(w8 + pl.off_cand);
+    // flag + counters are contiguous at the start of the workspace
+    cudaError_t e = cudaMemsetAsync(w8, 0, pl.off_thrT, stream);
+    if (e != cudaSuccess) return e;
+    for (uint32_t ph = 0; ph < pl.num_phases; ++ph) {
+        const MmaPhase& P = pl.phase[ph];
+        const bool last = ph + 1 == pl.num_phases;
+        if (P.tiles) {
+            MmaScanParams sp;
+            sp.hashes = d_hashes;
+            sp.queries = d_queries;
+            sp.thrT = thrT;
+            sp.thrK = thrK;
+            sp.cand = cand;
+            sp.cnt = cnt;
+            sp.N = N;
+            sp.row_base = row_base;
+            sp.Q = Q;
+            sp.words = W;
+            sp.cap = pl.cap;
+            sp.n_tile = pl.n_tile;
+            sp.num_qtiles = pl.num_qtiles;
+            sp.phase_tiles = P.tiles;
+            sp.tile_stride = P.stride;
+            sp.skip_mod = P.skip_mod;
+            sp.tiles_per_chunk = P.tiles_per_chunk;
+            sp.num_chunks = P.num_chunks;
+            sp.dense = ph == 0;
+            sp.a_stages = pl.a_stages;
+            sp.p_stages = pl.p_stages;
+            if (last && ev_scan_begin) {
+                e = cudaEventRecord(ev_scan_begin, stream);
+                if (e != cudaSuccess) return e;
+            }
+            e = launch_mma_scan(sp, (int)P.grid, pl.smem, stream);
+            if (e != cudaSuccess) return e;
+            if (last && ev_scan_end) {
+                e = cudaEventRecord(ev_scan_end, stream);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        MmaSelectParams se;
+        se.cand = cand;
+        se.cnt = cnt;
+        se.best = best;
+        se.thrT = thrT;
+        se.thrK = thrK;
+        se.overflow = flag;
+        se.out_rows = last ? d_rows : nullptr;
+        se.out_dists = last ? d_dists : nullptr;
+        se.out_keys = last ? d_keys : nullptr;
+        se.Q = Q;
+        se.Qpad = pl.q_pad;
+        se.k = k;
+        se.cap = pl.cap;
+        se.bits = W * 64;
+        se.fixed_cnt = ph == 0 ? (int)(P.tiles * kMmaTileRows) : -1;
+        se.first = ph == 0;
+        se.sort_cap = pl.sort_cap;
+        e = launch_mma_select(se, stream);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace nps

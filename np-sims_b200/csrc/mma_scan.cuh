@@ -1,0 +1,126 @@
+// mma_scan.cuh — K2T: batched Hamming scan on the 5th-gen tensor cores (tcgen05 + TMEM).
+//
+// Why tensor cores for an XOR+popcount loop.  For a BATCH of queries the scan
+//       d[i, q] = sum_w popc(H[i, w] ^ Q[q, w])
+// is a matrix product over {-1,+1}: with bit b encoded as (1 - 2b),  <h_i, q_j> = bits - 2 d.
+// On sm_100a the integer route costs 2 POPC per 64-bit word-pair on a 16-lane/clk/SM pipe
+// (profiles/r01_scan_topk_c2_popc.txt: XU pipe 56 % busy, DRAM 0.01 %), i.e. the batched scan is
+// compute-bound, not HBM-bound, and sm_100a has no native 1-bit MMA.  The
+// closest native tensor-core form is kind::f8f6f4 with E4M3 operands holding exactly +-1.0 and
+// FP32 accumulation in TMEM: every partial sum is an integer of magnitude <= bits < 2^24, so
+// the result is EXACT — bit-identical distances — at 8192 MAC/clk/SM instead of 8 word-pairs.
+// The signature table stays bit-packed in HBM/L2 (no 8x expansion of traffic): tiles are
+// expanded to E4M3 on chip, straight into the swizzled shared-memory operand layout.
+//
+// Kernel structure (one persistent CTA per SM, 14 warps, warp-specialised):
+//   warp 0      producer  : 1-D TMA bulk copies of bit-packed row tiles (128 rows) into a ring
+//   warp 1      MMA issuer: tcgen05.mma M=128 x N=n_tile x K=32, accumulators double-buffered in TMEM
+//   warps 2-5   expanders : bit-packed words -> E4M3 +-1 bytes, K-major SWIZZLE_128B operand tiles
+//                           (B = the query tile, once per work item; A = row tile, per K-block)
+//   warps 6-13  epilogue  : tcgen05.ld the 128 x n_tile dot products, threshold filter, append
+// Selection: the kernel does no top-k bookkeeping.  Each launch ("phase") filters against a
+// fixed per-query threshold (the exact k-th best key over the rows of all previous phases) and
+// appends survivors (key = dist << 40 | row) to a per-query candidate buffer; mma_select_kernel
+// then folds the candidates into the exact running top-k and tightens the threshold.  Phases
+// visit the row tiles of the table in an interleaved (strided) order, each phase ~G x larger
+// than everything before it, so the expected number of survivors per query and phase is ~k*G.
+#pragma once
+#include "tc.cuh"
+
+namespace nps {
+
+constexpr int kMmaThreads = 14 * 32;
+constexpr int kMmaTileRows = 128;         // UMMA M
+constexpr int kMmaKBlockBytes = 128;      // one swizzle row = 128 E4M3 = 128 signature bits = 2 words
+constexpr int kMmaAStageBytes = kMmaTileRows * kMmaKBlockBytes;   // 16 KB
+constexpr int kMmaHitsPerWarp = 64;
+constexpr int kMmaEpiWarps = 8;
+constexpr uint32_t kMmaMaxWords = 32;
+
+struct MmaScanParams {
+    const uint64_t* hashes;    // [N, W] bit-packed
+    const uint64_t* queries;   // [Q, W] bit-packed
+    const float* thrT;         // [Qpad]  pass iff dot >= thrT[q]   (-inf: everything, +inf: nothing)
+    const uint64_t* thrK;      // [Qpad]  exact test: key < thrK[q]
+    uint64_t* cand;            // [Q, cap] candidate keys
+    uint32_t* cnt;             // [Q] candidates appended this phase
+    unsigned long long N, row_base;
+    uint32_t Q, words, cap, n_tile, num_qtiles;
+    uint32_t phase_tiles;      // row tiles in this phase
+    uint32_t tile_stride;      // tile = j * tile_stride
+    uint32_t skip_mod;         // G: j runs over integers with j % G != 0 (0: j = i, first phase)
+    uint32_t tiles_per_chunk, num_chunks;
+    uint32_t dense;            // first phase: write every key at cand[q, i*128 + r], no filter
+    uint32_t a_stages, p_stages;
+};
+
+struct MmaSmem {
+    uint32_t b_off, a_off, p_off, p_stride, hitk_off, hitq_off, wcnt_off, bar_off, tmem_off, total;
+};
+__host__ __device__ inline uint32_t mma_kblocks(uint32_t words) { return (words + 1) / 2; }
+__host__ __device__ inline MmaSmem mma_smem_layout(uint32_t words, uint32_t n_tile, uint32_t a_stages,
+                                                   uint32_t p_stages) {
+    MmaSmem s;
+    uint32_t off = 0;
+    s.b_off = off;
+    off += mma_kblocks(words) * n_tile * kMmaKBlockBytes;
+    s.a_off = off;
+    off += a_stages * kMmaAStageBytes;
+    s.p_off = off;
+    s.p_stride = (kMmaTileRows * words * 8 + 127u) & ~127u;
+    off += p_stages * s.p_stride;
+    s.hitk_off = off;
+    off += kMmaEpiWarps * kMmaHitsPerWarp * 8;
+    s.hitq_off = off;
+    off += kMmaEpiWarps * kMmaHitsPerWarp * 4;
+    s.wcnt_off = off;
+    off += kMmaEpiWarps * 4;
+    off = (off + 7u) & ~7u;
+    s.bar_off = off;
+    off += (2 * p_stages + 2 * a_stages + 5) * 8;
+    s.tmem_off = off;
+    off += 8;
+    s.total = off + 1024;   // slack for the manual 1024-byte alignment of the base
+    return s;
+}
+
+struct MmaSelectParams {
+    uint64_t* cand;          // [Q, cap]
+    uint32_t* cnt;           // [Q]   (reset to 0)
+    uint64_t* best;          // [Q, k] running top-k keys, ascending, NPS_NONE padded (in/out)
+    float* thrT;             // [Qpad] (out)
+    uint64_t* thrK;          // [Qpad] (out)
+    uint32_t* overflow;      // [1] incremented once per query whose buffer overflowed
+    uint64_t* out_rows;      // final phase: decoded ids / distances / keys (any may be null)
+    uint64_t* out_dists;
+    uint64_t* out_keys;
+    uint32_t Q, Qpad, k, cap, bits;
+    int fixed_cnt;           // >= 0: dense phase, every query has exactly this many candidates
+    uint32_t first;          // first phase: `best` holds garbage, treat as empty
+    uint32_t sort_cap;       // shared-memory sort capacity (power of two >= k + cap)
+};
+
+cudaError_t launch_mma_scan(const MmaScanParams& p, int grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_mma_select(const MmaSelectParams& p, cudaStream_t stream);
+
+// ---- host-side plan: tile shape, candidate capacity, phase schedule -------------------------
+constexpr int kMmaMaxPhases = 24;
+struct MmaPhase {
+    uint32_t tiles, stride, skip_mod, tiles_per_chunk, num_chunks, grid;
+};
+struct MmaPlan {
+    uint32_t n_tile, num_qtiles, q_pad, cap, growth, a_stages, p_stages, smem, sort_cap, num_phases;
+    MmaPhase phase[kMmaMaxPhases];
+    // workspace carve-up (bytes from the workspace base)
+    size_t off_flag, off_cnt, off_thrT, off_thrK, off_best, off_cand, total;
+};
+// false if the tensor-core path does not apply to this shape (the caller uses the popc scan)
+bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_count, int smem_optin, MmaPlan* pl);
+// d_rows/d_dists/d_keys: any may be null.  ws: pl.total bytes, 256-byte aligned.  ws[0] (uint32)
+// counts the queries whose candidate buffer overflowed (results of those queries are not final).
+cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned long long N, uint32_t W,
+                          const uint64_t* d_queries, uint32_t Q, uint32_t k, unsigned long long row_base,
+                          uint64_t* d_rows, uint64_t* d_dists, uint64_t* d_keys, void* ws, cudaStream_t stream,
+                          cudaEvent_t ev_scan_begin, cudaEvent_t ev_scan_end);
+
+}  // namespace nps

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libnpsims_b200.so")
 NPS_OK, NPS_EINVAL, NPS_ECUDA, NPS_EWORKSPACE = 0, -1, -2, -3
 NPS_MAX_K, NPS_MAX_WORDS = 2048, 1024
 ORDER_CANONICAL, ORDER_REFERENCE = 0, 1
+SCAN_AUTO, SCAN_POPC, SCAN_MMA = 0, 1, 2
 PROJ_TF32X3, PROJ_TF32, PROJ_FP32_SIMT = 0, 1, 2
 
 if not os.path.exists(LIB_PATH):
@@ -34,6 +35,10 @@ _SIGS = {
     "nps_profile_last": (_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     "nps_last_scan_plan": (_int, [_vp]),
     "nps_launch_count": (ctypes.c_ulonglong, []),
+    "nps_set_scan_path": (_int, [_int]),
+    "nps_last_scan_path": (_int, []),
+    "nps_last_mma_plan": (_int, [_vp]),
+    "nps_top_n_overflow_count": (_int, [_vp, _vp, ctypes.POINTER(ctypes.c_uint32)]),
     "nps_host_hamming_top_k": (_int, [_vp, _vp, _u64, _u64, _u32, _vp]),
     "nps_host_hamming": (_int, [_vp, _vp, _u64, _u64, _vp]),
     "nps_index_create": (_int, [_vp, _u64, _u32, _int, ctypes.POINTER(_vp)]),
@@ -66,6 +71,38 @@ class ScanPlan(ctypes.Structure):
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class MmaPlan(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "n_tile", "num_qtiles", "cap", "growth", "a_stages", "smem_bytes", "num_phases", "last_tiles",
+        "last_tiles_per_chunk", "last_num_chunks", "last_grid", "reserved")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+
+
+def last_mma_plan() -> dict:
+    plan = MmaPlan()
+    check(_lib.nps_last_mma_plan(ctypes.byref(plan)))
+    return plan.as_dict()
+
+
+_scan_path = SCAN_AUTO
+
+
+def set_scan_path(path: int) -> int:
+    """Select the scan kernel family (SCAN_AUTO / SCAN_POPC / SCAN_MMA); returns the previous one."""
+    global _scan_path
+    check(_lib.nps_set_scan_path(path))
+    prev, _scan_path = _scan_path, path
+    return prev
+
+
+def overflow_count(ws_ptr: int, stream: int) -> int:
+    n = ctypes.c_uint32(0)
+    check(_lib.nps_top_n_overflow_count(ws_ptr, stream, ctypes.byref(n)))
+    return int(n.value)
 
 
 def last_scan_plan() -> dict:

@@ -34,6 +34,10 @@ def _cuda_local_keys(H, Q, k, row_base):
     with t.cuda.device(H.device):
         _lib.call("nps_hamming_top_n_keys", ptr(H), m, w, ptr(Q), q, k, int(row_base), ptr(keys), ptr(ws), ws_bytes,
                   stream_ptr())
+        from .ufuncs import _repair_overflow
+        _repair_overflow(lambda ws2, nb: _lib.call(
+            "nps_hamming_top_n_keys", ptr(H), m, w, ptr(Q), q, k, int(row_base), ptr(keys), ptr(ws2), nb,
+            stream_ptr()), ws, m, w, q, k, H.device)
     return keys
 
 

@@ -100,6 +100,9 @@ def hamming_top_n(hashes, query, n=10, return_distances=False, order="canonical"
             ws = t.empty(ws_bytes, dtype=t.uint8, device=H.device)
             _lib.call("nps_hamming_top_n", ptr(H), m, w, ptr(Q), q, n, int(row_base), ptr(rows), ptr(dists),
                       ptr(ws), ws_bytes, stream_ptr())
+            _repair_overflow(lambda ws2, nb: _lib.call(
+                "nps_hamming_top_n", ptr(H), m, w, ptr(Q), q, n, int(row_base), ptr(rows), ptr(dists), ptr(ws2), nb,
+                stream_ptr()), ws, m, w, q, n, H.device)
         else:
             if row_base:
                 raise ValueError("row_base is only supported with order='canonical'")
@@ -115,6 +118,24 @@ def hamming_top_n(hashes, query, n=10, return_distances=False, order="canonical"
     if return_distances:
         return _finish(rows, single, host), _finish(dists, single, host)
     return _finish(rows, single, host)
+
+
+def _repair_overflow(rerun, ws, m, w, q, n, device):
+    """Tensor-core scan only: its per-query candidate buffers are sized for ~4x the expected
+    number of survivors; if one overflowed (adversarial row order), redo the call on the
+    XOR+POPC scan, which has no such limit.  Costs one 4-byte D2H read per batched call."""
+    t = require_cuda()
+    if _lib.raw("nps_last_scan_path")() != _lib.SCAN_MMA:
+        return
+    if _lib.overflow_count(ptr(ws), stream_ptr()) == 0:
+        return
+    prev = _lib.set_scan_path(_lib.SCAN_POPC)
+    try:
+        nb = _lib.raw("nps_hamming_top_n_workspace_bytes")(m, w, q, n)
+        ws2 = t.empty(nb, dtype=t.uint8, device=device)
+        rerun(ws2, nb)
+    finally:
+        _lib.set_scan_path(prev)
 
 
 def hamming_top_10(hashes, query):
