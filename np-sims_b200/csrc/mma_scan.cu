@@ -1,37 +1,43 @@
 // mma_scan.cu — K2T kernels: tensor-core batched Hamming scan + candidate select.
 // See mma_scan.cuh for the design.  Replaces, for query batches, the scan bodies of
 // np_sims/ufunc.c:207-441 (XOR + popcount + queue insert) with an exact +-1 E4M3 GEMM.
+#include <cstdio>
+#include <cstdlib>
+
 #include "mma_scan.cuh"
 
 namespace nps {
 
-// 4 signature bits -> 4 E4M3 bytes: bit 0 -> +1.0 (0x38), bit 1 -> -1.0 (0xB8).
-// n * 0x10204080 places bit i of the nibble at bit 8*i+7 (the copies do not overlap).
-__device__ __forceinline__ uint32_t expand4(uint32_t nib) {
-    return ((nib * 0x10204080u) & 0x80808080u) | 0x38383838u;
+// 8 signature bits -> 8 E2M1 nibbles (one 32-bit word): bit 0 -> +1.0 (0x2), bit 1 -> -1.0 (0xA).
+// Three multiply+mask steps spread bit i to bit 4i+3 (the shifted copies never overlap).
+__device__ __forceinline__ uint32_t expand8(uint32_t byte) {
+    uint32_t y = (byte * 0x1001u) & 0x000F000Fu;     // b0-3 | b4-7 at bit 16
+    y = (y * 0x41u) & 0x03030303u;                   // two bits per byte
+    return ((y * 72u) & 0x88888888u) | 0x22222222u;  // bit i -> sign bit of nibble i; exponent = 1.0
 }
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// Expand one 128-bit K-block (words w0, w1) of operand row `r` into its 128-byte swizzled row.
-// tile_base: shared address of the [rows x 128 B] SWIZZLE_128B tile (1024-byte aligned).
-__device__ __forceinline__ void expand_row_kblock(uint32_t tile_base, uint32_t r, uint64_t w0, uint64_t w1,
-                                                  bool have0, bool have1) {
+// Expand 16-byte chunks [C0, C1) of one 256-bit K-block (words w[0..3], the first `nvalid` of which
+// exist) of operand row `r` into its 128-byte swizzled row.  Chunk c holds signature bits
+// [32c, 32c+32) of the K-block.  tile_base: shared address of the [rows x 128 B] SWIZZLE_128B
+// tile (1024-byte aligned).  Missing words become E2M1 zeros, which add nothing to the dot.
+template <int C0, int C1>
+__device__ __forceinline__ void expand_row_kblock(uint32_t tile_base, uint32_t r, const uint64_t (&w)[4],
+                                                  uint32_t nvalid) {
     const uint32_t r7 = r & 7u;
     const uint32_t row_base = tile_base + (r >> 3) * 1024u + r7 * 128u;
-    const uint32_t half[4] = {(uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32)};
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const uint32_t bits16 = (half[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
-        const bool have = c < 4 ? have0 : have1;
-        uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;     // E4M3 zero: contributes nothing to the dot
-        if (have) {
-            x0 = expand4(bits16 & 15u);
-            x1 = expand4((bits16 >> 4) & 15u);
-            x2 = expand4((bits16 >> 8) & 15u);
-            x3 = expand4(bits16 >> 12);
+    for (int c = C0; c < C1; ++c) {
+        const uint32_t h = (c & 1) ? (uint32_t)(w[c >> 1] >> 32) : (uint32_t)w[c >> 1];
+        uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+        if ((uint32_t)(c >> 1) < nvalid) {
+            x0 = expand8(h & 0xFFu);
+            x1 = expand8(__byte_perm(h, 0u, 0x4441u));
+            x2 = expand8(__byte_perm(h, 0u, 0x4442u));
+            x3 = expand8(h >> 24);
         }
         sts128(row_base + (((uint32_t)c ^ r7) << 4), x0, x1, x2, x3);
     }
@@ -62,6 +68,28 @@ __device__ __noinline__ void record_hit(const MmaScanParams& p, uint32_t q, uint
     }
 }
 
+// development aid: CTA 0 logs (clock, role, event) triples; role slots of 4096 events each
+#define NPS_TRACE(role, ev)                                                                        \
+    do {                                                                                           \
+        if (p.trace && blockIdx.x == 0 && trace_n < 4096u) {                                       \
+            p.trace[((role) * 4096u + trace_n) * 2u] = (unsigned long long)clock64();              \
+            p.trace[((role) * 4096u + trace_n) * 2u + 1u] = (ev);                                  \
+            ++trace_n;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+// Warp roles.  The hardware arbiter favours the highest warp id of a scheduler, so the two
+// single-thread roles whose latency paces the whole pipeline (MMA issue, TMA issue) sit on the
+// last two warps; measured: with the issuer on warp 1 a busy epilogue halved the MMA rate.
+constexpr int kWarpProducer = kMmaExpWarps + kMmaEpiWarps;
+constexpr int kWarpMma = kWarpProducer + 1;      // two issuer warps: kWarpMma (even tiles), kWarpMma + 1 (odd tiles)
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -69,13 +97,17 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
     uint8_t* smem = smem_raw + (base - raw);
     const uint32_t W = p.words, KB = mma_kblocks(W), NT = p.n_tile;
     const MmaSmem L = mma_smem_layout(W, NT, p.a_stages, p.p_stages);
-    const uint32_t AS = p.a_stages, PS = p.p_stages;
+    const uint32_t PS = p.p_stages;
+    // A ring: each MMA issuer owns RG (1 or 2) groups of GS K-block stages, so that every
+    // group barrier has exactly one consumer (mbarrier phase parity cannot alias).
+    const uint32_t GS = p.group_kb, RG = p.ring_per_issuer, NG = 2u * RG;
+    const uint32_t GPT = (KB + GS - 1) / GS;             // groups per row tile
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* p_full = bars;
     uint64_t* p_empty = p_full + PS;
-    uint64_t* a_full = p_empty + PS;
-    uint64_t* a_empty = a_full + AS;
-    uint64_t* acc_full = a_empty + AS;      // [2]
+    uint64_t* g_full = p_empty + PS;
+    uint64_t* g_empty = g_full + NG;
+    uint64_t* acc_full = g_empty + NG;      // [2]
     uint64_t* acc_empty = acc_full + 2;     // [2]
     uint64_t* b_full = acc_empty + 2;       // [1]
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
@@ -85,30 +117,41 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
     if (tid == 0) {
         for (uint32_t s = 0; s < PS; ++s) {
             mbar_init(&p_full[s], 1);
-            mbar_init(&p_empty[s], kMmaTileRows);
+            mbar_init(&p_empty[s], kMmaExpWarps);
         }
-        for (uint32_t s = 0; s < AS; ++s) {
-            mbar_init(&a_full[s], kMmaTileRows);
-            mbar_init(&a_empty[s], 1);
+        for (uint32_t s = 0; s < NG; ++s) {
+            mbar_init(&g_full[s], kMmaExpWarps);
+            mbar_init(&g_empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
             mbar_init(&acc_empty[b], kMmaEpiWarps);
         }
-        mbar_init(b_full, kMmaTileRows);
+        mbar_init(b_full, kMmaExpWarps);
         fence_mbar_init();
     }
     if (tid < kMmaEpiWarps) wcnt_s[tid] = 0;
-    if (warp == 1) tmem_alloc(tmem_ptr_s, 512);
+    if (warp == kWarpMma) tmem_alloc(tmem_ptr_s, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_s);
+    // Block scale factors: every byte of TMEM columns [kMmaSfCol, 512) = 0x7F = UE8M0 1.0, so the
+    // (layout-dependent) scale lookup of kind::mxf4 returns 1.0 for every row and K block.
+    if (warp < 4) {
+        for (uint32_t c = kMmaSfCol; c < 512u; c += 8u)
+            tmem_st8_fill(tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + c, 0x7F7F7F7Fu);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     const uint32_t total_items = p.num_chunks * p.num_qtiles;
     const uint32_t row_bytes = W * 8;
+    uint32_t trace_n = 0;
 
-    if (warp == 0) {
+    if (warp == kWarpProducer) {
         // =========================== producer: bit-packed row tiles ===========================
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
@@ -136,45 +179,72 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 }
             }
         }
-    } else if (warp == 1) {
-        // =========================== MMA issuer =================================================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc(0, 0, kMmaTileRows, NT);
-            const uint32_t ksteps_last = (W & 1u) ? 2u : 4u;
-            uint32_t as = 0, aph = 0, t_idx = 0, it_idx = 0;
-            for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x, ++it_idx) {
-                const uint32_t chunk = item / p.num_qtiles;
-                const uint32_t i0 = chunk * p.tiles_per_chunk;
-                const uint32_t i1 = min(i0 + p.tiles_per_chunk, p.phase_tiles);
-                mbar_wait(b_full, it_idx & 1u);
-                for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
-                    const uint32_t buf = t_idx & 1u;
-                    mbar_wait(&acc_empty[buf], ((t_idx >> 1) & 1u) ^ 1u);
+    } else if (warp >= kWarpMma) {
+        // =========================== MMA issuers ================================================
+        // Two warps, one per accumulator buffer (even / odd row tiles), each running converged
+        // with one elected lane issuing: while one sits in a barrier wait or in the stall that
+        // follows tcgen05.commit, the other keeps the tensor pipe fed.  Their MMA streams are
+        // independent (different accumulators, different A groups), so no order is required.
+        const uint32_t mw = warp - kWarpMma;
+        const uint32_t idesc = umma_idesc_mxf4(kMmaTileRows, NT);
+        const uint32_t sfa = tmem_base + kMmaSfCol, sfb = tmem_base + kMmaSfCol + 32u;
+        const uint64_t a_desc0 = umma_desc_k_sw128(base + L.a_off);
+        const uint64_t b_desc0 = umma_desc_k_sw128(base + L.b_off);
+        uint32_t t_idx = 0, it_idx = 0, lg = 0;   // lg: groups consumed by this issuer
+        for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x, ++it_idx) {
+            const uint32_t chunk = item / p.num_qtiles;
+            const uint32_t i0 = chunk * p.tiles_per_chunk;
+            const uint32_t i1 = min(i0 + p.tiles_per_chunk, p.phase_tiles);
+            bool b_ready = false;
+            for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
+                const uint32_t buf = t_idx & 1u;
+                if (buf != mw) continue;
+                if (!b_ready) {
+                    mbar_wait(b_full, it_idx & 1u);
+                    b_ready = true;
+                }
+                mbar_wait(&acc_empty[buf], ((t_idx >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                if (lane == 0) NPS_TRACE(mw ? 3 : 0, 1);   // accumulator free
+                const uint32_t d_tmem = tmem_base + buf * NT;
+                for (uint32_t g = 0; g < GPT; ++g, ++lg) {
+                    const uint32_t slot = mw * RG + (lg & (RG - 1u)), par = (lg >> (RG - 1u)) & 1u;
+                    mbar_wait(&g_full[slot], par);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * NT;
-                    for (uint32_t kb = 0; kb < KB; ++kb) {
-                        mbar_wait(&a_full[as], aph);
-                        tc_fence_after();
-                        const uint32_t a_addr = base + L.a_off + as * kMmaAStageBytes;
-                        const uint32_t b_addr = base + L.b_off + kb * NT * kMmaKBlockBytes;
-                        const uint32_t ks = (kb + 1 == KB) ? ksteps_last : 4u;
-                        for (uint32_t j = 0; j < ks; ++j)
-                            umma_f8(d_tmem, umma_desc_k_sw128(a_addr + j * 32u), umma_desc_k_sw128(b_addr + j * 32u),
-                                    idesc, (kb | j) != 0u);
-                        umma_commit(&a_empty[as]);     // A stage may be overwritten once these MMAs retire
-                        if (++as == AS) {
-                            as = 0;
-                            aph ^= 1u;
+                    if (lane == 0) NPS_TRACE(mw ? 3 : 0, 2);   // A group full
+                    if (elect_one()) {
+                        const uint32_t kb0 = g * GS, kb1 = min(kb0 + GS, KB);
+                        for (uint32_t kb = kb0; kb < kb1; ++kb) {
+                            const uint32_t stage = slot * GS + (kb - kb0);
+                            const uint64_t a_desc = a_desc0 + (uint64_t)((stage * kMmaAStageBytes) >> 4);
+                            const uint64_t b_desc = b_desc0 + (uint64_t)((kb * NT * kMmaKBlockBytes) >> 4);
+                            const uint32_t nw = min(4u, W - 4u * kb);   // one MMA (K = 64) per signature word
+                            for (uint32_t j = 0; j < nw && !(p.debug & 4u); ++j)
+                                umma_mxf4(d_tmem, a_desc + 2u * j, b_desc + 2u * j, idesc, sfa, sfb, (kb | j) != 0u);
                         }
+                        umma_commit(&g_empty[slot]);                  // group reusable once these MMAs retire
+                        if (g + 1 == GPT) umma_commit(&acc_full[buf]);   // accumulator complete -> epilogue
                     }
-                    umma_commit(&acc_full[buf]);       // accumulator complete -> epilogue
+                    __syncwarp();
+                    if (lane == 0) NPS_TRACE(mw ? 3 : 0, 3);   // issued + committed
                 }
             }
         }
-    } else if (warp < 6) {
-        // =========================== expanders: bits -> E4M3 operand tiles =======================
-        const uint32_t u = tid - 64;   // 0..127 = operand row
-        uint32_t as = 0, aph = 0, ps = 0, pph = 0, t_idx = 0;
+    } else if (warp < kMmaExpWarps) {
+        // =========================== expanders: bits -> E2M1 operand tiles =======================
+        // kMmaExpWarps/4 threads per operand row; with two, each expands half of the 128-byte row
+        constexpr int kParts = kMmaExpWarps / 4;
+        const uint32_t u = tid & 127u;               // operand row
+        const uint32_t part = tid >> 7;              // which slice of the 128-byte row
+        auto expand = [&](uint32_t tile_base, uint32_t r, const uint64_t (&w)[4], uint32_t nvalid) {
+            if constexpr (kParts == 1) {
+                expand_row_kblock<0, 8>(tile_base, r, w, nvalid);
+            } else {
+                if (part == 0) expand_row_kblock<0, 4>(tile_base, r, w, nvalid);
+                else expand_row_kblock<4, 8>(tile_base, r, w, nvalid);
+            }
+        };
+        uint32_t ps = 0, pph = 0, t_idx = 0, lg2[2] = {0, 0};   // lg2[mw]: groups produced for issuer mw
         for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x) {
             const uint32_t chunk = item / p.num_qtiles, qt = item - chunk * p.num_qtiles;
             const uint32_t q0 = qt * NT;
@@ -183,37 +253,50 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
             // B (query tile) is resident for the whole item; the previous item's MMAs must have
             // retired before it is overwritten.
             if (t_idx > 0) mbar_wait(&acc_full[(t_idx - 1) & 1u], ((t_idx - 1) >> 1) & 1u);
+            if (t_idx > 1) mbar_wait(&acc_full[(t_idx - 2) & 1u], ((t_idx - 2) >> 1) & 1u);
             for (uint32_t n = u; n < NT; n += kMmaTileRows) {
                 const bool valid = q0 + n < p.Q;
                 const uint64_t* src = p.queries + (size_t)(valid ? q0 + n : 0) * W;
                 for (uint32_t kb = 0; kb < KB; ++kb) {
-                    const bool h1 = 2 * kb + 1 < W;
-                    const uint64_t w0 = valid ? __ldg(src + 2 * kb) : 0ull;
-                    const uint64_t w1 = (valid && h1) ? __ldg(src + 2 * kb + 1) : 0ull;
-                    expand_row_kblock(base + L.b_off + kb * NT * kMmaKBlockBytes, n, w0, w1, valid, valid && h1);
+                    const uint32_t nw = valid ? min(4u, W - 4u * kb) : 0u;
+                    uint64_t w[4];
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) w[j] = j < nw ? __ldg(src + 4 * kb + j) : 0ull;
+                    expand(base + L.b_off + kb * NT * kMmaKBlockBytes, n, w, nw);
                 }
             }
             fence_proxy_async_smem();
-            mbar_arrive(b_full);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_full);
             for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
                 const unsigned long long row0 = (unsigned long long)phase_tile(p, i) * kMmaTileRows;
                 const bool valid = row0 + u < p.N;
                 mbar_wait(&p_full[ps], pph);
+                if (tid == 0) NPS_TRACE(1, 3);   // packed tile landed
                 const uint64_t* my = reinterpret_cast<const uint64_t*>(smem + L.p_off + ps * L.p_stride) + (size_t)u * W;
-                for (uint32_t kb = 0; kb < KB; ++kb) {
-                    const bool h1 = 2 * kb + 1 < W;
-                    const uint64_t w0 = valid ? my[2 * kb] : 0ull;
-                    const uint64_t w1 = (valid && h1) ? my[2 * kb + 1] : 0ull;
-                    mbar_wait(&a_empty[as], aph ^ 1u);
-                    expand_row_kblock(base + L.a_off + as * kMmaAStageBytes, u, w0, w1, valid, valid && h1);
-                    fence_proxy_async_smem();
-                    mbar_arrive(&a_full[as]);
-                    if (++as == AS) {
-                        as = 0;
-                        aph ^= 1u;
+                const uint32_t mw = t_idx & 1u;
+                uint32_t lg = mw ? lg2[1] : lg2[0];
+                for (uint32_t g = 0; g < GPT; ++g, ++lg) {
+                    const uint32_t slot = mw * RG + (lg & (RG - 1u)), par = (lg >> (RG - 1u)) & 1u;
+                    mbar_wait(&g_empty[slot], par ^ 1u);
+                    if (tid == 0) NPS_TRACE(1, 1);   // group free
+                    const uint32_t kb0 = g * GS, kb1 = min(kb0 + GS, KB);
+                    for (uint32_t kb = kb0; kb < kb1; ++kb) {
+                        const uint32_t nw = valid ? min(4u, W - 4u * kb) : 0u;
+                        uint64_t w[4];
+#pragma unroll
+                        for (uint32_t j = 0; j < 4; ++j) w[j] = j < nw ? my[4 * kb + j] : 0ull;
+                        if (!(p.debug & 2u))
+                            expand(base + L.a_off + (slot * GS + (kb - kb0)) * kMmaAStageBytes, u, w, nw);
                     }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&g_full[slot]);
+                    if (tid == 0) NPS_TRACE(1, 2);   // group written
                 }
-                mbar_arrive(&p_empty[ps]);
+                if (mw) lg2[1] = lg; else lg2[0] = lg;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_empty[ps]);
                 if (++ps == PS) {
                     ps = 0;
                     pph ^= 1u;
@@ -222,13 +305,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         }
     } else {
         // =========================== epilogue: filter + append ====================================
-        const uint32_t ew = warp - 6;                 // 0..7
+        const uint32_t ew = warp - kMmaExpWarps;
         const uint32_t quarter = warp & 3u;           // TMEM lanes this warp may read
         const uint32_t r_in_tile = quarter * 32u + lane;
         const uint32_t ngroups = NT / 32u;
-        const uint32_t g_split = (ngroups + 1u) / 2u;
-        const uint32_t g_begin = (ew < 4) ? 0u : g_split;
-        const uint32_t g_end = (ew < 4) ? g_split : ngroups;
+        constexpr uint32_t kColParts = kMmaEpiWarps / 4;
+        const uint32_t g_per = (ngroups + kColParts - 1u) / kColParts;
+        const uint32_t g_begin = min((ew >> 2) * g_per, ngroups);
+        const uint32_t g_end = min(g_begin + g_per, ngroups);
         uint64_t* hitk = reinterpret_cast<uint64_t*>(smem + L.hitk_off) + ew * kMmaHitsPerWarp;
         uint32_t* hitq = reinterpret_cast<uint32_t*>(smem + L.hitq_off) + ew * kMmaHitsPerWarp;
         uint32_t* wcnt = wcnt_s + ew;
@@ -246,8 +330,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 const uint64_t grow = p.row_base + row;
                 mbar_wait(&acc_full[buf], (t_idx >> 1) & 1u);
                 tc_fence_after();
+                if (ew == 0 && lane == 0) NPS_TRACE(2, 1);   // accumulator ready
                 for (uint32_t g = g_begin; g < g_end; ++g) {
                     uint32_t v[32];
+                    if (p.debug & 8u) continue;
                     tmem_ld32(tmem_base + ((quarter * 32u) << 16) + buf * NT + g * 32u, v);
                     const uint32_t qg = q0 + g * 32u;
                     if (p.dense) {
@@ -260,6 +346,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                                 p.cand[(size_t)(qg + j) * p.cap + slot] = valid ? ((d << kGlobalRowBits) | grow) : kNone;
                             }
                         }
+                        continue;
+                    }
+                    if (p.debug & 1u) {
+                        tmem_ld_wait();
                         continue;
                     }
                     float T[32];
@@ -294,6 +384,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                if (ew == 0 && lane == 0) NPS_TRACE(2, 2);   // accumulator released
                 // flush this warp's hit buffer: up to 32 global appends in flight at a time
                 if (!p.dense) {
                     const uint32_t n = min(*reinterpret_cast<volatile uint32_t*>(wcnt), (uint32_t)kMmaHitsPerWarp);
@@ -303,6 +394,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                         if (lane == 0) *reinterpret_cast<volatile uint32_t*>(wcnt) = 0;
                         __syncwarp();
                     }
+                    if (ew == 0 && lane == 0) NPS_TRACE(2, 3);   // flush done
                 }
             }
         }
@@ -310,7 +402,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == kWarpMma) tmem_dealloc(tmem_base, 512);
 }
 
 cudaError_t launch_mma_scan(const MmaScanParams& p, int grid, size_t smem, cudaStream_t stream) {
@@ -413,20 +505,44 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
     if (sm_count <= 0) sm_count = 148;
     if (smem_optin <= 0) smem_optin = 232448;
     // ---- operand tile: the widest query tile (multiple of 32, <= 256) that fits next to >= 2 A stages
-    const uint32_t want = ((Q < 256u ? Q : 256u) + 31u) & ~31u;
-    uint32_t n_tile = 0, a_stages = 0;
-    for (uint32_t nt = want; nt >= 32 && !n_tile; nt -= 32)
-        for (uint32_t as = 4; as >= 2; --as)
-            if (mma_smem_layout(W, nt, as, 2).total <= (uint32_t)smem_optin) {
+    const uint32_t want = ((Q < kMmaMaxNTile ? Q : kMmaMaxNTile) + 31u) & ~31u;
+    // A ring: each of the two MMA issuers owns RG groups of GS K-block stages; a group is filled,
+    // consumed and released as a unit (one barrier wait + one tcgen05.commit).  Prefer whole-tile
+    // groups; for wide signatures use smaller groups rather than a narrow query tile.
+    const uint32_t KB = mma_kblocks(W);
+    uint32_t n_tile = 0, gs_best = 0, rg_best = 0;
+    for (uint32_t gs = KB;; gs = (gs + 1) / 2) {
+        for (uint32_t nt = want; nt >= 32; nt -= 32) {
+            if (nt < 128 && nt < want && gs > 1) break;          // try smaller groups before narrow tiles
+            uint32_t rg = 0;
+            for (uint32_t cand = 2; cand >= 1; --cand)
+                if (mma_smem_layout(W, nt, gs * 2 * cand, 2).total <= (uint32_t)smem_optin) {
+                    rg = cand;
+                    break;
+                }
+            if (rg) {
                 n_tile = nt;
-                a_stages = as;
+                gs_best = gs;
+                rg_best = rg;
                 break;
             }
+        }
+        if (n_tile || gs == 1) break;
+    }
     if (!n_tile) return false;
+    if (const char* e = getenv("NPS_MMA_GROUPS")) {     // development: "GS,RG"
+        uint32_t gs = 0, rg = 0;
+        if (sscanf(e, "%u,%u", &gs, &rg) == 2 && gs && (rg == 1 || rg == 2)) {
+            gs_best = gs;
+            rg_best = rg;
+        }
+    }
     pl->n_tile = n_tile;
-    pl->a_stages = a_stages;
+    pl->group_kb = gs_best;
+    pl->ring_per_issuer = rg_best;
+    pl->a_stages = gs_best * 2 * rg_best;
     pl->p_stages = 2;
-    pl->smem = mma_smem_layout(W, n_tile, a_stages, 2).total;
+    pl->smem = mma_smem_layout(W, n_tile, pl->a_stages, 2).total;
     pl->num_qtiles = (Q + n_tile - 1) / n_tile;
     pl->q_pad = pl->num_qtiles * n_tile;
     // ---- candidate capacity and phase growth: expected survivors per phase ~ k * growth <= cap / 4
@@ -544,6 +660,18 @@ cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned 
             sp.dense = ph == 0;
             sp.a_stages = pl.a_stages;
             sp.p_stages = pl.p_stages;
+            sp.group_kb = pl.group_kb;
+            sp.ring_per_issuer = pl.ring_per_issuer;
+            sp.trace = nullptr;
+            const char* trace_path = getenv("NPS_MMA_TRACE");
+            if (trace_path && last) {
+                cudaMalloc(&sp.trace, 4 * 4096 * 16);
+                cudaMemsetAsync(sp.trace, 0, 4 * 4096 * 16, stream);
+            }
+            {
+                const char* dbg = getenv("NPS_MMA_DEBUG");
+                sp.debug = (dbg && !sp.dense) ? (uint32_t)atoi(dbg) : 0u;
+            }
             if (last && ev_scan_begin) {
                 e = cudaEventRecord(ev_scan_begin, stream);
                 if (e != cudaSuccess) return e;
@@ -553,6 +681,16 @@ cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned 
             if (last && ev_scan_end) {
                 e = cudaEventRecord(ev_scan_end, stream);
                 if (e != cudaSuccess) return e;
+            }
+            if (sp.trace) {
+                static unsigned long long host_trace[4 * 4096 * 2];
+                cudaStreamSynchronize(stream);
+                cudaMemcpy(host_trace, sp.trace, sizeof(host_trace), cudaMemcpyDeviceToHost);
+                cudaFree(sp.trace);
+                if (FILE* f = fopen(trace_path, "wb")) {
+                    fwrite(host_trace, 1, sizeof(host_trace), f);
+                    fclose(f);
+                }
             }
         }
         MmaSelectParams se;

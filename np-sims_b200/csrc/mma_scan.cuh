@@ -29,12 +29,21 @@
 
 namespace nps {
 
-constexpr int kMmaThreads = 14 * 32;
+#ifndef NPS_MMA_EXP_WARPS
+#define NPS_MMA_EXP_WARPS 8
+#endif
+#ifndef NPS_MMA_EPI_WARPS
+#define NPS_MMA_EPI_WARPS 8
+#endif
+constexpr int kMmaExpWarps = NPS_MMA_EXP_WARPS;   // 4 or 8: threads per operand row = kMmaExpWarps / 4
+constexpr int kMmaEpiWarps = NPS_MMA_EPI_WARPS;   // 4 or 8
+constexpr int kMmaThreads = (3 + kMmaExpWarps + kMmaEpiWarps) * 32;   // + producer + 2 MMA issuers
 constexpr int kMmaTileRows = 128;         // UMMA M
-constexpr int kMmaKBlockBytes = 128;      // one swizzle row = 128 E4M3 = 128 signature bits = 2 words
+constexpr int kMmaKBlockBytes = 128;      // one swizzle row = 256 E2M1 = 256 signature bits = 4 words
+constexpr uint32_t kMmaSfCol = 448;       // TMEM columns [448, 512): block scale factors (all 1.0)
+constexpr uint32_t kMmaMaxNTile = 224;    // 2 accumulators x 224 columns = 448
 constexpr int kMmaAStageBytes = kMmaTileRows * kMmaKBlockBytes;   // 16 KB
 constexpr int kMmaHitsPerWarp = 64;
-constexpr int kMmaEpiWarps = 8;
 constexpr uint32_t kMmaMaxWords = 32;
 
 struct MmaScanParams {
@@ -52,12 +61,15 @@ struct MmaScanParams {
     uint32_t tiles_per_chunk, num_chunks;
     uint32_t dense;            // first phase: write every key at cand[q, i*128 + r], no filter
     uint32_t a_stages, p_stages;
+    uint32_t group_kb, ring_per_issuer;   // A ring: 2 x ring_per_issuer groups of group_kb K-block stages
+    unsigned long long* trace; // development only: per-role event timestamps of CTA 0
+    uint32_t debug;            // development only: 1 = no epilogue filter, 2 = no expansion, 4 = no MMA
 };
 
 struct MmaSmem {
     uint32_t b_off, a_off, p_off, p_stride, hitk_off, hitq_off, wcnt_off, bar_off, tmem_off, total;
 };
-__host__ __device__ inline uint32_t mma_kblocks(uint32_t words) { return (words + 1) / 2; }
+__host__ __device__ inline uint32_t mma_kblocks(uint32_t words) { return (words + 3) / 4; }
 __host__ __device__ inline MmaSmem mma_smem_layout(uint32_t words, uint32_t n_tile, uint32_t a_stages,
                                                    uint32_t p_stages) {
     MmaSmem s;
@@ -109,7 +121,7 @@ struct MmaPhase {
     uint32_t tiles, stride, skip_mod, tiles_per_chunk, num_chunks, grid;
 };
 struct MmaPlan {
-    uint32_t n_tile, num_qtiles, q_pad, cap, growth, a_stages, p_stages, smem, sort_cap, num_phases;
+    uint32_t n_tile, num_qtiles, q_pad, cap, growth, a_stages, p_stages, group_kb, ring_per_issuer, smem, sort_cap, num_phases;
     MmaPhase phase[kMmaMaxPhases];
     // workspace carve-up (bytes from the workspace base)
     size_t off_flag, off_cnt, off_thrT, off_thrK, off_best, off_cand, total;

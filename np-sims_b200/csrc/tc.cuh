@@ -63,6 +63,29 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::mxf4: E2M1 (4-bit) operands packed two per byte, K = 64 per instruction, block-32 UE8M0
+// scale factors read from TMEM.  Instruction descriptor (cute::UMMA::InstrDescriptorBlockScaled):
+__host__ __device__ constexpr uint32_t umma_idesc_mxf4(uint32_t M, uint32_t N) {
+    return (1u << 7) | (1u << 10)            // A, B format: E2M1
+           | ((N >> 3) << 17) | (1u << 23)   // N; scale format UE8M0
+           | ((M >> 4) << 24);               // M; scale-factor ids 0; K = 64
+}
+__device__ __forceinline__ void umma_mxf4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
+// registers -> TMEM: this warp's 32 lanes x 8 consecutive columns, all set to v
+__device__ __forceinline__ void tmem_st8_fill(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(v)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // all MMAs issued so far by this thread -> arrive on an mbarrier when they complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
