@@ -44,6 +44,8 @@ def _compile(unit, force: bool, verbose: bool):
     if (not force and os.path.exists(obj)
             and os.path.getmtime(obj) > max(os.path.getmtime(src_path), _newest_header())):
         return obj, False
+    if os.environ.get("NPS_DEV"):      # development build: event trace + cycle accounting in mma_scan.cu
+        defs = [*defs, "-DNPS_MMA_DEV"]
     cmd = [NVCC, *FLAGS, *defs, "-c", src_path, "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

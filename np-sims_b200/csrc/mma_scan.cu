@@ -8,14 +8,12 @@
 
 namespace nps {
 
-// 8 signature bits -> 8 E2M1 nibbles (one 32-bit word): bit 0 -> +1.0 (0x2), bit 1 -> -1.0 (0xA).
-// Three multiply+mask steps spread bit i to bit 4i+3 (the shifted copies never overlap).
-__device__ __forceinline__ uint32_t expand8(uint32_t byte) {
-    uint32_t y = (byte * 0x1001u) & 0x000F000Fu;     // b0-3 | b4-7 at bit 16
-    y = (y * 0x41u) & 0x03030303u;                   // two bits per byte
-    return ((y * 72u) & 0x88888888u) | 0x22222222u;  // bit i -> sign bit of nibble i; exponent = 1.0
-}
-
+// Bit-packed signature word -> E2M1 operand words, without spreading any bits.
+// An E2M1 nibble is  sign | exp1 exp0 | mant ; 0b0010 = +1.0, 0b1010 = -1.0.  Every nibble of the
+// raw 32-bit word already carries four signature bits, so  ((R << s) & 0x88888888) | 0x22222222
+// turns bit (3 - s) of every nibble into the sign of a +-1.0 element: four shifts give four operand
+// words holding all 32 bits.  The K order of the elements is a fixed permutation of the bit order,
+// the same for signatures and queries, so dot products (= bits - 2 * Hamming distance) are unchanged.
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -32,14 +30,56 @@ __device__ __forceinline__ void expand_row_kblock(uint32_t tile_base, uint32_t r
 #pragma unroll
     for (int c = C0; c < C1; ++c) {
         const uint32_t h = (c & 1) ? (uint32_t)(w[c >> 1] >> 32) : (uint32_t)w[c >> 1];
-        uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+        uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;     // missing words: E2M1 zeros add nothing to the dot
         if ((uint32_t)(c >> 1) < nvalid) {
-            x0 = expand8(h & 0xFFu);
-            x1 = expand8(__byte_perm(h, 0u, 0x4441u));
-            x2 = expand8(__byte_perm(h, 0u, 0x4442u));
-            x3 = expand8(h >> 24);
+            x0 = (h & 0x88888888u) | 0x22222222u;
+            x1 = ((h << 1) & 0x88888888u) | 0x22222222u;
+            x2 = ((h << 2) & 0x88888888u) | 0x22222222u;
+            x3 = ((h << 3) & 0x88888888u) | 0x22222222u;
         }
         sts128(row_base + (((uint32_t)c ^ r7) << 4), x0, x1, x2, x3);
+    }
+}
+
+// ---- thresholds folded into the GEMM -------------------------------------------------------
+// The filter "dot >= T" (T = bits - 2 * k-th best distance, an even integer) is evaluated by the
+// tensor core: one extra K = 64 slice whose A elements are all 4.0 and whose B row n spells -T_n / 4
+// as a sum of E2M1 values, so the accumulator holds  dot - T  and the epilogue only looks at sign
+// bits.  4 * {0, .5, 1, 1.5, 2, 3, 4, 6} = {0, 2, 4, 6, 8, 12, 16, 24}: |T| / 2 = 12 * n12 + rem with
+// rem < 12 written as at most two of {1, 2, 3, 4, 6, 8}.
+__device__ __forceinline__ float clamp_thr(float t) {
+    return fminf(fmaxf(t, -(float)kMmaThrRange), (float)kMmaThrRange);   // +-inf -> never / always
+}
+__device__ __forceinline__ void encode_thr(float t, uint32_t (&out)[8]) {
+    const int T = (int)clamp_thr(t);
+    const uint32_t m = (uint32_t)(T < 0 ? -T : T) >> 1;
+    const int n12 = (int)(m / 12u);
+    const uint32_t rem = m - 12u * (uint32_t)n12;
+    // E2M1 codes of the one or two remainder elements, packed as c1 | c2 << 4, indexed by rem
+    uint32_t c1, c2;
+    switch (rem) {
+        case 0: c1 = 0; c2 = 0; break;
+        case 1: c1 = 1; c2 = 0; break;
+        case 2: c1 = 2; c2 = 0; break;
+        case 3: c1 = 3; c2 = 0; break;
+        case 4: c1 = 4; c2 = 0; break;
+        case 5: c1 = 4; c2 = 1; break;
+        case 6: c1 = 5; c2 = 0; break;
+        case 7: c1 = 5; c2 = 1; break;
+        case 8: c1 = 6; c2 = 0; break;
+        case 9: c1 = 6; c2 = 1; break;
+        case 10: c1 = 6; c2 = 2; break;
+        default: c1 = 6; c2 = 3; break;
+    }
+    const uint32_t sign = T > 0 ? 0x88888888u : 0u;   // B holds -T: negative elements for positive T
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int full = min(max(n12 - 8 * w, 0), 8);
+        uint32_t x = full == 8 ? 0x77777777u : (0x77777777u & ((1u << (4 * full)) - 1u));
+        const int p1 = n12 - 8 * w, p2 = p1 + 1;
+        if (p1 >= 0 && p1 < 8) x |= c1 << (4 * p1);
+        if (p2 >= 0 && p2 < 8) x |= c2 << (4 * p2);
+        out[w] = x | sign;
     }
 }
 
@@ -53,22 +93,54 @@ __device__ __forceinline__ void global_append(const MmaScanParams& p, uint32_t q
     if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = key;
 }
 
-// slow path of the epilogue: exact test against the k-th best key, then stage the survivor in
-// this warp's shared-memory buffer (flushed with up to 32 global atomics in flight per warp)
-__device__ __noinline__ void record_hit(const MmaScanParams& p, uint32_t q, uint64_t key, uint32_t* wcnt,
-                                        uint64_t* hitk, uint32_t* hitq) {
-    if (key < __ldg(p.thrK + q)) {
-        const uint32_t idx = atomicAdd(wcnt, 1u);
-        if (idx < (uint32_t)kMmaHitsPerWarp) {
-            hitk[idx] = key;
-            hitq[idx] = q;
-        } else {
-            global_append(p, q, key);
-        }
+// Slow path of the epilogue: a value  dot - T  is non-negative, i.e. the row passed the distance
+// filter (distance <= k-th best distance; ties are sorted out by mma_select_kernel).  All that
+// happens while the accumulator is still held is staging the raw 32-bit value and its position
+// (lane, column) in this warp's shared-memory buffer: six predicated instructions per column, no
+// calls and no branches, because this code is cold in the instruction cache (measured: a version
+// with one out-of-line call per column cost ~4000 cycles per group in fetch stalls alone).
+// Decoding (distance, key) and the global append happen at flush time, after the accumulator went
+// back to the MMA issuer.  Slot kMmaHitsPerWarp is a dump slot for overflowing entries.
+template <int J>
+__device__ __forceinline__ void stage_if_hit(uint32_t x, uint32_t code, uint32_t* wcnt, uint2* hits) {
+    if ((int)x >= 0) {
+        const uint32_t i = min(atomicAdd(wcnt, 1u), (uint32_t)kMmaHitsPerWarp);
+        hits[i] = make_uint2(x, code + (uint32_t)(J << 8));
+    }
+}
+template <int J0, int I = 0>
+__device__ __forceinline__ void stage_hits8(const uint32_t (&v)[32], uint32_t code, uint32_t* wcnt, uint2* hits) {
+    if constexpr (I < 8) {
+        stage_if_hit<J0 + I>(v[J0 + I], code, wcnt, hits);
+        stage_hits8<J0, I + 1>(v, code, wcnt, hits);
     }
 }
 
+// Exact fallback when a warp's staging buffer overflowed during a tile (early phases, whose
+// thresholds are still loose): the warp's accumulator columns are read again and every survivor is
+// appended directly.  Cold and slow by design (rolled loop, values parked in local memory).
+__device__ __noinline__ void rescan_group(uint32_t taddr, const float* thr, uint32_t q_first, uint64_t grow, int bits,
+                                          bool valid, uint32_t* g_cnt, uint64_t* g_cand, uint32_t cap) {
+    uint32_t v[32];
+    tmem_ld32(taddr, v);      // .sync.aligned: the whole warp is here, converged
+    tmem_ld_wait();
+    if (valid) {
+#pragma unroll 1
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t x = v[j];
+            if ((int)x >= 0) {
+                const int dot = (int)(__uint_as_float(x) + thr[j]);
+                const uint64_t key = ((uint64_t)((bits - dot) >> 1) << kGlobalRowBits) | grow;
+                const uint32_t pos = atomicAdd(g_cnt + q_first + j, 1u);
+                if (pos < cap) g_cand[(size_t)(q_first + j) * cap + pos] = key;
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // development aid: CTA 0 logs (clock, role, event) triples; role slots of 4096 events each
+#ifdef NPS_MMA_DEV
 #define NPS_TRACE(role, ev)                                                                        \
     do {                                                                                           \
         if (p.trace && blockIdx.x == 0 && trace_n < 4096u) {                                       \
@@ -77,6 +149,11 @@ __device__ __noinline__ void record_hit(const MmaScanParams& p, uint32_t q, uint
             ++trace_n;                                                                             \
         }                                                                                          \
     } while (0)
+#define NPS_DEV(...) __VA_ARGS__
+#else
+#define NPS_TRACE(role, ev) do { } while (0)
+#define NPS_DEV(...)
+#endif
 
 // Warp roles.  The hardware arbiter favours the highest warp id of a scheduler, so the two
 // single-thread roles whose latency paces the whole pipeline (MMA issue, TMA issue) sit on the
@@ -84,12 +161,21 @@ __device__ __noinline__ void record_hit(const MmaScanParams& p, uint32_t q, uint
 constexpr int kWarpProducer = kMmaExpWarps + kMmaEpiWarps;
 constexpr int kWarpMma = kWarpProducer + 1;      // two issuer warps: kWarpMma (even tiles), kWarpMma + 1 (odd tiles)
 
+// Register redistribution between warpgroups (setmaxnreg): the kernel launches with 96 registers
+// per thread; expanders and the single-thread roles give registers back, the epilogue takes them.
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+constexpr int kRegsExpander = 88, kRegsMisc = 40;
+constexpr int kRegsEpilogue =
+    ((kMmaThreads * 96 - kMmaExpWarps * 32 * kRegsExpander - 4 * 32 * kRegsMisc) / (kMmaEpiWarps * 32)) / 8 * 8;
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
     return pred != 0;
 }
 
+template <bool kDense>
 __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -131,6 +217,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         fence_mbar_init();
     }
     if (tid < kMmaEpiWarps) wcnt_s[tid] = 0;
+    for (uint32_t i = tid; i < kMmaTileRows * 32u / 4u; i += kMmaThreads)
+        reinterpret_cast<uint32_t*>(smem + L.athr_off)[i] = 0x66666666u;   // E2M1 4.0 in every element
+    fence_proxy_async_smem();
     if (warp == kWarpMma) tmem_alloc(tmem_ptr_s, 512);
     tc_fence_before();
     __syncthreads();
@@ -149,10 +238,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
 
     const uint32_t total_items = p.num_chunks * p.num_qtiles;
     const uint32_t row_bytes = W * 8;
-    uint32_t trace_n = 0;
+    NPS_DEV(uint32_t trace_n = 0;)
 
     if (warp == kWarpProducer) {
         // =========================== producer: bit-packed row tiles ===========================
+        reg_dec<kRegsMisc>();
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
             for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -179,17 +269,23 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 }
             }
         }
+    } else if (warp == kWarpMma + 2) {
+        // idle warp: completes the last warpgroup so that setmaxnreg is warpgroup-uniform
+        reg_dec<kRegsMisc>();
     } else if (warp >= kWarpMma) {
         // =========================== MMA issuers ================================================
         // Two warps, one per accumulator buffer (even / odd row tiles), each running converged
         // with one elected lane issuing: while one sits in a barrier wait or in the stall that
         // follows tcgen05.commit, the other keeps the tensor pipe fed.  Their MMA streams are
         // independent (different accumulators, different A groups), so no order is required.
+        reg_dec<kRegsMisc>();
         const uint32_t mw = warp - kWarpMma;
         const uint32_t idesc = umma_idesc_mxf4(kMmaTileRows, NT);
         const uint32_t sfa = tmem_base + kMmaSfCol, sfb = tmem_base + kMmaSfCol + 32u;
         const uint64_t a_desc0 = umma_desc_k_sw128(base + L.a_off);
         const uint64_t b_desc0 = umma_desc_k_sw128(base + L.b_off);
+        const uint64_t athr_desc = umma_desc_k_noswizzle(base + L.athr_off, 128u, 256u);
+        const uint64_t bthr_desc = umma_desc_k_noswizzle(base + L.bthr_off, 128u, 256u);
         uint32_t t_idx = 0, it_idx = 0, lg = 0;   // lg: groups consumed by this issuer
         for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x, ++it_idx) {
             const uint32_t chunk = item / p.num_qtiles;
@@ -223,7 +319,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                                 umma_mxf4(d_tmem, a_desc + 2u * j, b_desc + 2u * j, idesc, sfa, sfb, (kb | j) != 0u);
                         }
                         umma_commit(&g_empty[slot]);                  // group reusable once these MMAs retire
-                        if (g + 1 == GPT) umma_commit(&acc_full[buf]);   // accumulator complete -> epilogue
+                        if (g + 1 == GPT) {
+                            if (!p.dense) umma_mxf4(d_tmem, athr_desc, bthr_desc, idesc, sfa, sfb, 1u);   // ... - T
+                            umma_commit(&acc_full[buf]);              // accumulator complete -> epilogue
+                        }
                     }
                     __syncwarp();
                     if (lane == 0) NPS_TRACE(mw ? 3 : 0, 3);   // issued + committed
@@ -233,6 +332,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
     } else if (warp < kMmaExpWarps) {
         // =========================== expanders: bits -> E2M1 operand tiles =======================
         // kMmaExpWarps/4 threads per operand row; with two, each expands half of the 128-byte row
+        reg_dec<kRegsExpander>();
         constexpr int kParts = kMmaExpWarps / 4;
         const uint32_t u = tid & 127u;               // operand row
         const uint32_t part = tid >> 7;              // which slice of the 128-byte row
@@ -263,6 +363,15 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
 #pragma unroll
                     for (uint32_t j = 0; j < 4; ++j) w[j] = j < nw ? __ldg(src + 4 * kb + j) : 0ull;
                     expand(base + L.b_off + kb * NT * kMmaKBlockBytes, n, w, nw);
+                }
+            }
+            if (!p.dense && part == 0) {
+                for (uint32_t n = u; n < NT; n += kMmaTileRows) {
+                    uint32_t e[8];
+                    encode_thr(__ldg(p.thrT + q0 + n), e);
+                    const uint32_t dst = base + L.bthr_off + (n >> 3) * 256u + (n & 7u) * 16u;
+                    sts128(dst, e[0], e[1], e[2], e[3]);
+                    sts128(dst + 128u, e[4], e[5], e[6], e[7]);
                 }
             }
             fence_proxy_async_smem();
@@ -305,6 +414,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         }
     } else {
         // =========================== epilogue: filter + append ====================================
+        // Each warp owns 32 accumulator rows (its TMEM lane quarter) x a contiguous run of 32-column
+        // groups.  Fast path per group: one tcgen05.ld (issued one group ahead), 8 broadcast
+        // LDS.128 of the warp-private thresholds, 32 compares on four independent predicate chains.
+        reg_inc<kRegsEpilogue>();
         const uint32_t ew = warp - kMmaExpWarps;
         const uint32_t quarter = warp & 3u;           // TMEM lanes this warp may read
         const uint32_t r_in_tile = quarter * 32u + lane;
@@ -313,32 +426,47 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         const uint32_t g_per = (ngroups + kColParts - 1u) / kColParts;
         const uint32_t g_begin = min((ew >> 2) * g_per, ngroups);
         const uint32_t g_end = min(g_begin + g_per, ngroups);
-        uint64_t* hitk = reinterpret_cast<uint64_t*>(smem + L.hitk_off) + ew * kMmaHitsPerWarp;
-        uint32_t* hitq = reinterpret_cast<uint32_t*>(smem + L.hitq_off) + ew * kMmaHitsPerWarp;
+        uint2* hits = reinterpret_cast<uint2*>(smem + L.hitk_off) + ew * (kMmaHitsPerWarp + 1);
+        float* thr_s = reinterpret_cast<float*>(smem + L.thr_off) + ew * (kMmaMaxNTile / 32u / kColParts + 1u) * 32u;
         uint32_t* wcnt = wcnt_s + ew;
         const int bits = (int)(W * 64u);
         uint32_t t_idx = 0;
+        NPS_DEV(long long prof_wait = 0, prof_tile = 0, prof_slow = 0, prof_flush = 0; uint32_t prof_nslow = 0;
+                const bool prof_on = p.trace != nullptr && blockIdx.x == 0;)
+        uint32_t pend_q = 0xFFFFFFFFu, pend_pos = 0;   // append whose slot reservation is still in flight
+        uint64_t pend_key = 0;
         for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x) {
             const uint32_t chunk = item / p.num_qtiles, qt = item - chunk * p.num_qtiles;
             const uint32_t q0 = qt * NT;
             const uint32_t i0 = chunk * p.tiles_per_chunk;
             const uint32_t i1 = min(i0 + p.tiles_per_chunk, p.phase_tiles);
+            if constexpr (!kDense) {   // this warp's thresholds for the item's query tile
+                __syncwarp();
+                for (uint32_t g = g_begin; g < g_end; ++g)
+                    thr_s[(g - g_begin) * 32u + lane] = clamp_thr(__ldg(p.thrT + q0 + g * 32u + lane));
+                __syncwarp();
+            }
             for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
                 const uint32_t buf = t_idx & 1u;
                 const unsigned long long row = (unsigned long long)phase_tile(p, i) * kMmaTileRows + r_in_tile;
                 const bool valid = row < p.N;
                 const uint64_t grow = p.row_base + row;
+                const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * NT;
+                NPS_DEV(const long long pc0 = prof_on ? clock64() : 0;)
                 mbar_wait(&acc_full[buf], (t_idx >> 1) & 1u);
                 tc_fence_after();
+                NPS_DEV(const long long pc1 = prof_on ? clock64() : 0; prof_wait += pc1 - pc0;)
                 if (ew == 0 && lane == 0) NPS_TRACE(2, 1);   // accumulator ready
-                for (uint32_t g = g_begin; g < g_end; ++g) {
-                    uint32_t v[32];
-                    if (p.debug & 8u) continue;
-                    tmem_ld32(tmem_base + ((quarter * 32u) << 16) + buf * NT + g * 32u, v);
-                    const uint32_t qg = q0 + g * 32u;
-                    if (p.dense) {
+
+                if constexpr (kDense) {
+                    // first phase: every distance of the tile goes to its fixed slot of the buffer
+                    const size_t slot = (size_t)i * kMmaTileRows + r_in_tile;
+#pragma unroll 1
+                    for (uint32_t g = g_begin; g < g_end; ++g) {
+                        uint32_t v[32];
+                        tmem_ld32(t_addr + g * 32u, v);
                         tmem_ld_wait();
-                        const size_t slot = (size_t)i * kMmaTileRows + r_in_tile;
+                        const uint32_t qg = q0 + g * 32u;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if (qg + j < p.Q) {
@@ -346,58 +474,117 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                                 p.cand[(size_t)(qg + j) * p.cap + slot] = valid ? ((d << kGlobalRowBits) | grow) : kNone;
                             }
                         }
-                        continue;
                     }
-                    if (p.debug & 1u) {
-                        tmem_ld_wait();
-                        continue;
-                    }
-                    float T[32];
-                    const float4* tp = reinterpret_cast<const float4*>(p.thrT + qg);
+                } else if (!(p.debug & 8u)) {
+                    // Bit i of the result: quarter i (8 columns) of this lane's 32 values  dot - T  holds a
+                    // non-negative one (sign bit clear).  16 three-input ANDs.
+                    auto test = [&](const uint32_t (&v)[32]) -> uint32_t {
+                        uint32_t m = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 t4 = __ldg(tp + j);
-                        T[4 * j + 0] = t4.x;
-                        T[4 * j + 1] = t4.y;
-                        T[4 * j + 2] = t4.z;
-                        T[4 * j + 3] = t4.w;
-                    }
-                    tmem_ld_wait();
-                    bool any = false;
+                        for (int qd = 0; qd < 4; ++qd) {
+                            uint32_t acc = v[8 * qd] & v[8 * qd + 1];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) any |= __uint_as_float(v[j]) >= T[j];
-                    any = any && valid;
-                    if (__any_sync(0xffffffffu, any)) {
-                        if (any) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                if (__uint_as_float(v[j]) >= T[j]) {
-                                    const uint64_t d = (uint64_t)((bits - (int)__uint_as_float(v[j])) >> 1);
-                                    const uint64_t key = (d << kGlobalRowBits) | grow;
-                                    record_hit(p, qg + j, key, wcnt, hitk, hitq);
-                                }
-                            }
+                            for (int j = 2; j < 8; j += 2) acc &= v[8 * qd + j] & v[8 * qd + j + 1];
+                            m |= (acc >> 31 ^ 1u) << qd;
                         }
+                        return (valid && !(p.debug & 1u)) ? m : 0u;
+                    };
+                    auto slow = [&](const uint32_t (&v)[32], uint32_t m, uint32_t g) {
+                        if (__any_sync(0xffffffffu, m != 0u)) {
+                            NPS_DEV(const long long s0 = prof_on ? clock64() : 0;)
+                            const uint32_t code = lane | ((g - g_begin) << 13);   // + column-in-group << 8
+                            if (m & 1u) stage_hits8<0>(v, code, wcnt, hits);
+                            if (m & 2u) stage_hits8<8>(v, code, wcnt, hits);
+                            if (m & 4u) stage_hits8<16>(v, code, wcnt, hits);
+                            if (m & 8u) stage_hits8<24>(v, code, wcnt, hits);
+                            __syncwarp();
+                            NPS_DEV(if (prof_on) {
+                                prof_slow += clock64() - s0;
+                                ++prof_nslow;
+                            })
+                        }
+                    };
+                    uint32_t va[32], vb[32];
+                    uint32_t g = g_begin;
+                    if (g < g_end) {
+                        tmem_ld32(t_addr + g * 32u, va);
+                        tmem_ld_wait();
+                    }
+                    while (g < g_end) {
+                        if (g + 1 < g_end) tmem_ld32(t_addr + (g + 1) * 32u, vb);
+                        const uint32_t any_a = test(va);
+                        if (g + 1 < g_end) tmem_ld_wait();
+                        slow(va, any_a, g);
+                        if (g + 1 >= g_end) break;
+                        if (g + 2 < g_end) tmem_ld32(t_addr + (g + 2) * 32u, va);
+                        const uint32_t any_b = test(vb);
+                        if (g + 2 < g_end) tmem_ld_wait();
+                        slow(vb, any_b, g + 1);
+                        g += 2;
+                    }
+                    // staging overflow (loose early-phase thresholds): redo this warp's columns exactly
+                    if (*reinterpret_cast<volatile uint32_t*>(wcnt) > (uint32_t)kMmaHitsPerWarp) {
+                        for (uint32_t gg = g_begin; gg < g_end; ++gg)
+                            rescan_group(t_addr + gg * 32u, thr_s + (gg - g_begin) * 32u, q0 + gg * 32u, grow, bits, valid,
+                                         p.cnt, p.cand, p.cap);
+                        __syncwarp();
+                        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(wcnt) = 0;
                         __syncwarp();
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                NPS_DEV(const long long pc2 = prof_on ? clock64() : 0; prof_tile += pc2 - pc1;)
                 if (ew == 0 && lane == 0) NPS_TRACE(2, 2);   // accumulator released
-                // flush this warp's hit buffer: up to 32 global appends in flight at a time
-                if (!p.dense) {
-                    const uint32_t n = min(*reinterpret_cast<volatile uint32_t*>(wcnt), (uint32_t)kMmaHitsPerWarp);
+                // Flush this warp's hit buffer, one entry per lane.  The atomic that reserves the
+                // slot is issued now, the dependent store one tile later (pend_*), so the ~1 us
+                // round trip of the returning atomic is never waited for.
+                if constexpr (!kDense) {
+                    NPS_DEV(const long long f0 = prof_on ? clock64() : 0;)
+                    if (pend_q != 0xFFFFFFFFu) {
+                        if (pend_pos < p.cap) p.cand[(size_t)pend_q * p.cap + pend_pos] = pend_key;
+                        pend_q = 0xFFFFFFFFu;
+                    }
+                    const uint32_t n = *reinterpret_cast<volatile uint32_t*>(wcnt);   // <= kMmaHitsPerWarp here
                     if (n) {
-                        for (uint32_t e = lane; e < n; e += 32) global_append(p, hitq[e], hitk[e]);
+                        // decode a staged entry: (dot - T, lane | column << 8) -> (query, key)
+                        auto decode = [&](uint32_t e, uint32_t& q, uint64_t& key) {
+                            const uint2 h = hits[e];
+                            const uint32_t col = h.y >> 8;   // column within this warp's groups
+                            const int dot = (int)(__uint_as_float(h.x) + thr_s[col]);
+                            const uint64_t r = grow - lane + (h.y & 31u);
+                            q = q0 + g_begin * 32u + col;
+                            key = ((uint64_t)((bits - dot) >> 1) << kGlobalRowBits) | r;
+                        };
+                        for (uint32_t e = lane + 32u; e < n; e += 32u) {   // rare: more than 32 staged entries
+                            uint32_t q;
+                            uint64_t key;
+                            decode(e, q, key);
+                            global_append(p, q, key);
+                        }
+                        if (lane < n) {
+                            decode(lane, pend_q, pend_key);
+                            pend_pos = atomicAdd(p.cnt + pend_q, 1u);
+                        }
                         __syncwarp();
                         if (lane == 0) *reinterpret_cast<volatile uint32_t*>(wcnt) = 0;
                         __syncwarp();
                     }
-                    if (ew == 0 && lane == 0) NPS_TRACE(2, 3);   // flush done
+                    NPS_DEV(if (prof_on) prof_flush += clock64() - f0;)
                 }
             }
         }
+        if (pend_q != 0xFFFFFFFFu && pend_pos < p.cap) p.cand[(size_t)pend_q * p.cap + pend_pos] = pend_key;
+        NPS_DEV(if (prof_on && lane == 0) {   // role slot 3 is shared with issuer 1: use its tail
+            unsigned long long* o = p.trace + (3u * 4096u + 4000u + ew * 8u) * 2u;
+            o[0] = (unsigned long long)prof_wait;
+            o[1] = (unsigned long long)prof_tile;
+            o[2] = (unsigned long long)prof_slow;
+            o[3] = (unsigned long long)prof_flush;
+            o[4] = prof_nslow;
+            o[5] = t_idx;
+        })
     }
 
     tc_fence_before();
@@ -406,9 +593,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
 }
 
 cudaError_t launch_mma_scan(const MmaScanParams& p, int grid, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(mma_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = p.dense ? mma_scan_kernel<true> : mma_scan_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    mma_scan_kernel<<<grid, kMmaThreads, smem, stream>>>(p);
+    kern<<<grid, kMmaThreads, smem, stream>>>(p);
     count_launch();
     return cudaGetLastError();
 }
@@ -555,31 +743,39 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
     pl->cap = cap;
     pl->growth = growth;
     pl->sort_cap = pow2_ceil(k + cap);
-    // ---- phases: tile strides G^(P-1), ..., G, 1; the first (dense) phase must fit the buffer
+    // ---- phases: nested tile subsets {t : t mod 2^e == 0}, e decreasing to 0.  The first (dense)
+    // phase must fit the candidate buffer; early phases grow by `growth` (cheap, but their loose
+    // thresholds let ~k * growth rows per query through), the last three only double, which keeps
+    // the share of accumulator groups with a survivor (the epilogue's slow path) near 10 %.
     const unsigned long long T = (N + kMmaTileRows - 1) / kMmaTileRows;
     if (T > 0x7FFFFFFFull) return false;
     const uint32_t tiles0_max = cap / kMmaTileRows;
-    uint32_t strides[kMmaMaxPhases];
-    uint32_t np = 1;
-    strides[0] = 1;
-    while ((T + strides[np - 1] - 1) / strides[np - 1] > tiles0_max) {
+    uint32_t e0 = 0;
+    while (((T + (1ull << e0) - 1) >> e0) > tiles0_max) ++e0;
+    uint32_t gshift = 0;
+    while ((2u << gshift) <= growth) ++gshift;        // growth rounded down to a power of two
+    if (gshift < 1) gshift = 1;
+    uint32_t exps[kMmaMaxPhases];
+    uint32_t np = 0;
+    exps[np++] = e0;
+    for (uint32_t e = e0; e > 0;) {
+        const uint32_t step = e <= 3 ? 1u : (e - 3 < gshift ? e - 3 : gshift);
+        e -= step;
         if (np == kMmaMaxPhases) return false;
-        const unsigned long long nxt = (unsigned long long)strides[np - 1] * growth;
-        if (nxt > 0x7FFFFFFFull) return false;
-        strides[np] = (uint32_t)nxt;
-        ++np;
+        exps[np++] = e;
     }
     pl->num_phases = np;
     for (uint32_t ph = 0; ph < np; ++ph) {
         MmaPhase& P = pl->phase[ph];
-        P.stride = strides[np - 1 - ph];
+        P.stride = 1u << exps[ph];
         const uint32_t J = (uint32_t)((T + P.stride - 1) / P.stride);
         if (ph == 0) {
             P.skip_mod = 0;
             P.tiles = J;
         } else {
-            P.skip_mod = growth;
-            P.tiles = J - (J + growth - 1) / growth;
+            const uint32_t g = 1u << (exps[ph - 1] - exps[ph]);
+            P.skip_mod = g;
+            P.tiles = J - (J + g - 1) / g;
         }
         // chunks: balance waves of (chunk, query tile) items over the SMs; ~1.5 tiles of fixed
         // cost per item (query-tile expansion + pipeline drain)
@@ -645,6 +841,7 @@ cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned 
             sp.thrK = thrK;
             sp.cand = cand;
             sp.cnt = cnt;
+            sp.overflow = flag;
             sp.N = N;
             sp.row_base = row_base;
             sp.Q = Q;

@@ -37,14 +37,15 @@ namespace nps {
 #endif
 constexpr int kMmaExpWarps = NPS_MMA_EXP_WARPS;   // 4 or 8: threads per operand row = kMmaExpWarps / 4
 constexpr int kMmaEpiWarps = NPS_MMA_EPI_WARPS;   // 4 or 8
-constexpr int kMmaThreads = (3 + kMmaExpWarps + kMmaEpiWarps) * 32;   // + producer + 2 MMA issuers
+constexpr int kMmaThreads = (4 + kMmaExpWarps + kMmaEpiWarps) * 32;   // + producer + 2 MMA issuers + 1 idle (full warpgroup)
 constexpr int kMmaTileRows = 128;         // UMMA M
 constexpr int kMmaKBlockBytes = 128;      // one swizzle row = 256 E2M1 = 256 signature bits = 4 words
 constexpr uint32_t kMmaSfCol = 448;       // TMEM columns [448, 512): block scale factors (all 1.0)
 constexpr uint32_t kMmaMaxNTile = 224;    // 2 accumulators x 224 columns = 448
 constexpr int kMmaAStageBytes = kMmaTileRows * kMmaKBlockBytes;   // 16 KB
 constexpr int kMmaHitsPerWarp = 64;
-constexpr uint32_t kMmaMaxWords = 32;
+constexpr uint32_t kMmaMaxWords = 23;      // |dot - threshold| must stay inside the folded-threshold range
+constexpr int kMmaThrRange = 1510;         // thresholds are clamped to +-this (even); > 64 * 23 bits
 
 struct MmaScanParams {
     const uint64_t* hashes;    // [N, W] bit-packed
@@ -53,6 +54,7 @@ struct MmaScanParams {
     const uint64_t* thrK;      // [Qpad]  exact test: key < thrK[q]
     uint64_t* cand;            // [Q, cap] candidate keys
     uint32_t* cnt;             // [Q] candidates appended this phase
+    uint32_t* overflow;        // [1] bumped if a warp's staging buffer overflowed (results then not final)
     unsigned long long N, row_base;
     uint32_t Q, words, cap, n_tile, num_qtiles;
     uint32_t phase_tiles;      // row tiles in this phase
@@ -67,7 +69,8 @@ struct MmaScanParams {
 };
 
 struct MmaSmem {
-    uint32_t b_off, a_off, p_off, p_stride, hitk_off, hitq_off, wcnt_off, bar_off, tmem_off, total;
+    uint32_t b_off, a_off, athr_off, bthr_off, p_off, p_stride, hitk_off, hitq_off, thr_off, wcnt_off, bar_off, tmem_off,
+        total;
 };
 __host__ __device__ inline uint32_t mma_kblocks(uint32_t words) { return (words + 3) / 4; }
 __host__ __device__ inline MmaSmem mma_smem_layout(uint32_t words, uint32_t n_tile, uint32_t a_stages,
@@ -78,13 +81,18 @@ __host__ __device__ inline MmaSmem mma_smem_layout(uint32_t words, uint32_t n_ti
     off += mma_kblocks(words) * n_tile * kMmaKBlockBytes;
     s.a_off = off;
     off += a_stages * kMmaAStageBytes;
+    s.athr_off = off;   // threshold operand tiles (no-swizzle K-major, one K = 64 slice): A = 4.0 everywhere,
+    off += kMmaTileRows * 32;
+    s.bthr_off = off;   // B row n = -(threshold of query n) / 4 spelled in E2M1 elements
+    off += n_tile * 32;
     s.p_off = off;
     s.p_stride = (kMmaTileRows * words * 8 + 127u) & ~127u;
     off += p_stages * s.p_stride;
     s.hitk_off = off;
-    off += kMmaEpiWarps * kMmaHitsPerWarp * 8;
+    off += kMmaEpiWarps * (kMmaHitsPerWarp + 1) * 8;   // (accumulator bits, position code) + 1 overflow slot
     s.hitq_off = off;
-    off += kMmaEpiWarps * kMmaHitsPerWarp * 4;
+    s.thr_off = off;   // per epilogue warp: thresholds of its column groups
+    off += kMmaEpiWarps * (kMmaMaxNTile / 32u / (kMmaEpiWarps / 4) + 1u) * 32u * 4u;
     s.wcnt_off = off;
     off += kMmaEpiWarps * 4;
     off = (off + 7u) & ~7u;

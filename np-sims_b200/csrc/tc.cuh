@@ -35,6 +35,18 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// K-major operand WITHOUT swizzle (cute::UMMA INTERLEAVE): 8-row x 16-byte core matrices stored
+// contiguously (128 B); lbo = byte distance between the two 16-byte K chunks of one MMA, sbo =
+// byte distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc_k_noswizzle(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
 // ---- instruction descriptor (kind::f8f6f4 / kind::tf32 / kind::f16), FP32 accumulate ----------
 // a_fmt/b_fmt: f8f6f4: 0 = E4M3, 1 = E5M2;  tf32 kind: 2 = TF32;  f16 kind: 0 = F16, 1 = BF16
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t a_fmt, uint32_t b_fmt, uint32_t M, uint32_t N) {
