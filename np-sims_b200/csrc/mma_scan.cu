@@ -93,40 +93,47 @@ __device__ __forceinline__ void global_append(const MmaScanParams& p, uint32_t q
     if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = key;
 }
 
-// Slow path of the epilogue: a value  dot - T  is non-negative, i.e. the row passed the distance
-// filter (distance <= k-th best distance; ties are sorted out by mma_select_kernel).  All that
-// happens while the accumulator is still held is staging the raw 32-bit value and its position
-// (lane, column) in this warp's shared-memory buffer: six predicated instructions per column, no
-// calls and no branches, because this code is cold in the instruction cache (measured: a version
-// with one out-of-line call per column cost ~4000 cycles per group in fetch stalls alone).
-// Decoding (distance, key) and the global append happen at flush time, after the accumulator went
-// back to the MMA issuer.  Slot kMmaHitsPerWarp is a dump slot for overflowing entries.
+// Slow path of the epilogue: some value  dot - T  of the group is non-negative, i.e. a row passed
+// the distance filter (distance <= k-th best distance; ties are sorted out by mma_select_kernel).
+// While the accumulator is still held, the survivors are only compacted into this warp's
+// shared-memory staging buffer as (raw accumulator bits, lane | column << 8): the whole warp walks
+// the columns of the flagged 8-column quarters together, one vote per column, slots handed out
+// from a warp-uniform register counter — no atomics, no divergence, no calls (this code is cold in
+// the instruction cache; a version with one out-of-line call per column cost ~4000 cycles per
+// group in fetch stalls, one with a shared-memory atomic per survivor ~2000).  Decoding
+// (distance, key) and the global append happen at flush time, after the accumulator went back to
+// the MMA issuer.
 template <int J>
-__device__ __forceinline__ void stage_if_hit(uint32_t x, uint32_t code, uint32_t* wcnt, uint2* hits) {
-    if ((int)x >= 0) {
-        const uint32_t i = min(atomicAdd(wcnt, 1u), (uint32_t)kMmaHitsPerWarp);
-        hits[i] = make_uint2(x, code + (uint32_t)(J << 8));
+__device__ __forceinline__ void stage_column(uint32_t x, uint32_t code, uint32_t& wn, uint2* hits, uint32_t lane_lt) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, (int)x >= 0);
+    if (mask) {   // warp-uniform
+        if ((int)x >= 0) {
+            const uint32_t slot = min(wn + __popc(mask & lane_lt), (uint32_t)kMmaHitsPerWarp);
+            hits[slot] = make_uint2(x, code + (uint32_t)(J << 8));
+        }
+        wn += __popc(mask);
     }
 }
 template <int J0, int I = 0>
-__device__ __forceinline__ void stage_hits8(const uint32_t (&v)[32], uint32_t code, uint32_t* wcnt, uint2* hits) {
+__device__ __forceinline__ void stage_hits8(const uint32_t (&v)[56], bool mine, uint32_t code, uint32_t& wn, uint2* hits,
+                                            uint32_t lane_lt) {
     if constexpr (I < 8) {
-        stage_if_hit<J0 + I>(v[J0 + I], code, wcnt, hits);
-        stage_hits8<J0, I + 1>(v, code, wcnt, hits);
+        stage_column<J0 + I>(mine ? v[J0 + I] : 0x80000000u, code, wn, hits, lane_lt);
+        stage_hits8<J0, I + 1>(v, mine, code, wn, hits, lane_lt);
     }
 }
 
 // Exact fallback when a warp's staging buffer overflowed during a tile (early phases, whose
 // thresholds are still loose): the warp's accumulator columns are read again and every survivor is
 // appended directly.  Cold and slow by design (rolled loop, values parked in local memory).
-__device__ __noinline__ void rescan_group(uint32_t taddr, const float* thr, uint32_t q_first, uint64_t grow, int bits,
-                                          bool valid, uint32_t* g_cnt, uint64_t* g_cand, uint32_t cap) {
+__device__ __noinline__ void rescan_group(uint32_t taddr, const float* thr, uint32_t q_first, int ncols, uint64_t grow,
+                                          int bits, bool valid, uint32_t* g_cnt, uint64_t* g_cand, uint32_t cap) {
     uint32_t v[32];
     tmem_ld32(taddr, v);      // .sync.aligned: the whole warp is here, converged
     tmem_ld_wait();
     if (valid) {
 #pragma unroll 1
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < ncols; ++j) {
             const uint32_t x = v[j];
             if ((int)x >= 0) {
                 const int dot = (int)(__uint_as_float(x) + thr[j]);
@@ -155,9 +162,11 @@ __device__ __noinline__ void rescan_group(uint32_t taddr, const float* thr, uint
 #define NPS_DEV(...)
 #endif
 
-// Warp roles.  The hardware arbiter favours the highest warp id of a scheduler, so the two
-// single-thread roles whose latency paces the whole pipeline (MMA issue, TMA issue) sit on the
-// last two warps; measured: with the issuer on warp 1 a busy epilogue halved the MMA rate.
+// Warp roles, in order of warp id: epilogue [0, 16), expanders [16, 24), producer, two MMA issuers,
+// one idle warp.  The hardware arbiter favours the highest warp id of a scheduler, so the roles
+// whose latency paces the pipeline come last: the single-thread issuers, then the expanders
+// (measured: with the expanders on the lowest ids, a tile's expansion took ~1900 cycles for ~150
+// instructions per thread because the waiting epilogue warps kept winning the issue slots).
 constexpr int kWarpProducer = kMmaExpWarps + kMmaEpiWarps;
 constexpr int kWarpMma = kWarpProducer + 1;      // two issuer warps: kWarpMma (even tiles), kWarpMma + 1 (odd tiles)
 
@@ -165,9 +174,10 @@ constexpr int kWarpMma = kWarpProducer + 1;      // two issuer warps: kWarpMma (
 // per thread; expanders and the single-thread roles give registers back, the epilogue takes them.
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-constexpr int kRegsExpander = 88, kRegsMisc = 40;
+constexpr int kRegsExpander = 64, kRegsMisc = 32;
+constexpr int kRegsLaunch = (65536 / kMmaThreads) / 8 * 8;   // what __launch_bounds__(kMmaThreads, 1) allows
 constexpr int kRegsEpilogue =
-    ((kMmaThreads * 96 - kMmaExpWarps * 32 * kRegsExpander - 4 * 32 * kRegsMisc) / (kMmaEpiWarps * 32)) / 8 * 8;
+    ((kMmaThreads * kRegsLaunch - kMmaExpWarps * 32 * kRegsExpander - 4 * 32 * kRegsMisc) / (kMmaEpiWarps * 32)) / 8 * 8;
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -329,13 +339,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 }
             }
         }
-    } else if (warp < kMmaExpWarps) {
+    } else if (warp >= kMmaEpiWarps) {
         // =========================== expanders: bits -> E2M1 operand tiles =======================
         // kMmaExpWarps/4 threads per operand row; with two, each expands half of the 128-byte row
         reg_dec<kRegsExpander>();
         constexpr int kParts = kMmaExpWarps / 4;
-        const uint32_t u = tid & 127u;               // operand row
-        const uint32_t part = tid >> 7;              // which slice of the 128-byte row
+        const uint32_t u = (tid - kMmaEpiWarps * 32) & 127u;   // operand row
+        const uint32_t part = (tid - kMmaEpiWarps * 32) >> 7;  // which slice of the 128-byte row
         auto expand = [&](uint32_t tile_base, uint32_t r, const uint64_t (&w)[4], uint32_t nvalid) {
             if constexpr (kParts == 1) {
                 expand_row_kblock<0, 8>(tile_base, r, w, nvalid);
@@ -381,14 +391,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 const unsigned long long row0 = (unsigned long long)phase_tile(p, i) * kMmaTileRows;
                 const bool valid = row0 + u < p.N;
                 mbar_wait(&p_full[ps], pph);
-                if (tid == 0) NPS_TRACE(1, 3);   // packed tile landed
+                if (u == 0 && part == 0) NPS_TRACE(1, 3);   // packed tile landed
                 const uint64_t* my = reinterpret_cast<const uint64_t*>(smem + L.p_off + ps * L.p_stride) + (size_t)u * W;
                 const uint32_t mw = t_idx & 1u;
                 uint32_t lg = mw ? lg2[1] : lg2[0];
                 for (uint32_t g = 0; g < GPT; ++g, ++lg) {
                     const uint32_t slot = mw * RG + (lg & (RG - 1u)), par = (lg >> (RG - 1u)) & 1u;
                     mbar_wait(&g_empty[slot], par ^ 1u);
-                    if (tid == 0) NPS_TRACE(1, 1);   // group free
+                    if (u == 0 && part == 0) NPS_TRACE(1, 1);   // group free
                     const uint32_t kb0 = g * GS, kb1 = min(kb0 + GS, KB);
                     for (uint32_t kb = kb0; kb < kb1; ++kb) {
                         const uint32_t nw = valid ? min(4u, W - 4u * kb) : 0u;
@@ -398,10 +408,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                         if (!(p.debug & 2u))
                             expand(base + L.a_off + (slot * GS + (kb - kb0)) * kMmaAStageBytes, u, w, nw);
                     }
+                    if (u == 0 && part == 0) NPS_TRACE(1, 4);   // group expanded (stores issued)
                     fence_proxy_async_smem();
+                    if (u == 0 && part == 0) NPS_TRACE(1, 5);   // proxy fence done
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&g_full[slot]);
-                    if (tid == 0) NPS_TRACE(1, 2);   // group written
+                    if (u == 0 && part == 0) NPS_TRACE(1, 2);   // group written
                 }
                 if (mw) lg2[1] = lg; else lg2[0] = lg;
                 __syncwarp();
@@ -414,21 +426,20 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         }
     } else {
         // =========================== epilogue: filter + append ====================================
-        // Each warp owns 32 accumulator rows (its TMEM lane quarter) x a contiguous run of 32-column
-        // groups.  Fast path per group: one tcgen05.ld (issued one group ahead), 8 broadcast
-        // LDS.128 of the warp-private thresholds, 32 compares on four independent predicate chains.
+        // 16 warps = 4 TMEM lane quarters (32 accumulator rows each) x 4 column parts (n_tile / 4
+        // queries each).  Per tile and warp: ONE tcgen05.ld.x64 (measured: 16 warps x one x64 load
+        // read a tile out in ~500 cycles, 8 warps x four pipelined x32 loads in ~900), 28 three-input
+        // ANDs over the sign bits of  dot - T , one warp reduce.
         reg_inc<kRegsEpilogue>();
-        const uint32_t ew = warp - kMmaExpWarps;
+        const uint32_t ew = warp;
         const uint32_t quarter = warp & 3u;           // TMEM lanes this warp may read
         const uint32_t r_in_tile = quarter * 32u + lane;
-        const uint32_t ngroups = NT / 32u;
-        constexpr uint32_t kColParts = kMmaEpiWarps / 4;
-        const uint32_t g_per = (ngroups + kColParts - 1u) / kColParts;
-        const uint32_t g_begin = min((ew >> 2) * g_per, ngroups);
-        const uint32_t g_end = min(g_begin + g_per, ngroups);
+        const uint32_t cpw = NT / 4u;                 // columns (queries) per warp: 8, 16, ..., 56
+        const uint32_t c0 = (ew >> 2) * cpw;
+        const uint32_t qmask = (1u << (cpw / 8u)) - 1u;   // 8-column quarters that exist
         uint2* hits = reinterpret_cast<uint2*>(smem + L.hitk_off) + ew * (kMmaHitsPerWarp + 1);
-        float* thr_s = reinterpret_cast<float*>(smem + L.thr_off) + ew * (kMmaMaxNTile / 32u / kColParts + 1u) * 32u;
-        uint32_t* wcnt = wcnt_s + ew;
+        float* thr_s = reinterpret_cast<float*>(smem + L.thr_off) + ew * 64u;
+        const uint32_t lane_lt = (1u << lane) - 1u;
         const int bits = (int)(W * 64u);
         uint32_t t_idx = 0;
         NPS_DEV(long long prof_wait = 0, prof_tile = 0, prof_slow = 0, prof_flush = 0; uint32_t prof_nslow = 0;
@@ -437,13 +448,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         uint64_t pend_key = 0;
         for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x) {
             const uint32_t chunk = item / p.num_qtiles, qt = item - chunk * p.num_qtiles;
-            const uint32_t q0 = qt * NT;
+            const uint32_t q0 = qt * NT + c0;          // first query of this warp's columns
             const uint32_t i0 = chunk * p.tiles_per_chunk;
             const uint32_t i1 = min(i0 + p.tiles_per_chunk, p.phase_tiles);
             if constexpr (!kDense) {   // this warp's thresholds for the item's query tile
                 __syncwarp();
-                for (uint32_t g = g_begin; g < g_end; ++g)
-                    thr_s[(g - g_begin) * 32u + lane] = clamp_thr(__ldg(p.thrT + q0 + g * 32u + lane));
+                for (uint32_t c = lane; c < cpw; c += 32u) thr_s[c] = clamp_thr(__ldg(p.thrT + q0 + c));
                 __syncwarp();
             }
             for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
@@ -451,85 +461,64 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 const unsigned long long row = (unsigned long long)phase_tile(p, i) * kMmaTileRows + r_in_tile;
                 const bool valid = row < p.N;
                 const uint64_t grow = p.row_base + row;
-                const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * NT;
+                const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * NT + c0;
+                uint32_t staged = 0;   // survivors of this tile waiting in the staging buffer
                 NPS_DEV(const long long pc0 = prof_on ? clock64() : 0;)
                 mbar_wait(&acc_full[buf], (t_idx >> 1) & 1u);
                 tc_fence_after();
                 NPS_DEV(const long long pc1 = prof_on ? clock64() : 0; prof_wait += pc1 - pc0;)
                 if (ew == 0 && lane == 0) NPS_TRACE(2, 1);   // accumulator ready
 
+                uint32_t v[56];
+                tmem_ld32_at<0>(t_addr, v);          // 56 columns = x32 + x16 + x8, one wait; columns beyond cpw
+                tmem_ld16_at<32>(t_addr + 32u, v);   // belong to the neighbouring warp: read, then ignored
+                tmem_ld8_at<48>(t_addr + 48u, v);
+                tmem_ld_wait();
                 if constexpr (kDense) {
                     // first phase: every distance of the tile goes to its fixed slot of the buffer
                     const size_t slot = (size_t)i * kMmaTileRows + r_in_tile;
-#pragma unroll 1
-                    for (uint32_t g = g_begin; g < g_end; ++g) {
-                        uint32_t v[32];
-                        tmem_ld32(t_addr + g * 32u, v);
-                        tmem_ld_wait();
-                        const uint32_t qg = q0 + g * 32u;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (qg + j < p.Q) {
-                                const uint64_t d = (uint64_t)((bits - (int)__uint_as_float(v[j])) >> 1);
-                                p.cand[(size_t)(qg + j) * p.cap + slot] = valid ? ((d << kGlobalRowBits) | grow) : kNone;
-                            }
+                    for (int j = 0; j < 56; ++j) {
+                        if ((uint32_t)j < cpw && q0 + j < p.Q) {
+                            const uint64_t d = (uint64_t)((bits - (int)__uint_as_float(v[j])) >> 1);
+                            p.cand[(size_t)(q0 + j) * p.cap + slot] = valid ? ((d << kGlobalRowBits) | grow) : kNone;
                         }
                     }
                 } else if (!(p.debug & 8u)) {
-                    // Bit i of the result: quarter i (8 columns) of this lane's 32 values  dot - T  holds a
-                    // non-negative one (sign bit clear).  16 three-input ANDs.
-                    auto test = [&](const uint32_t (&v)[32]) -> uint32_t {
-                        uint32_t m = 0;
+                    // bit i of m: 8-column quarter i holds a non-negative  dot - T  (sign bit clear)
+                    uint32_t m = 0;
 #pragma unroll
-                        for (int qd = 0; qd < 4; ++qd) {
-                            uint32_t acc = v[8 * qd] & v[8 * qd + 1];
+                    for (int qd = 0; qd < 7; ++qd) {
+                        uint32_t acc = v[8 * qd] & v[8 * qd + 1];
 #pragma unroll
-                            for (int j = 2; j < 8; j += 2) acc &= v[8 * qd + j] & v[8 * qd + j + 1];
-                            m |= (acc >> 31 ^ 1u) << qd;
-                        }
-                        return (valid && !(p.debug & 1u)) ? m : 0u;
-                    };
-                    auto slow = [&](const uint32_t (&v)[32], uint32_t m, uint32_t g) {
-                        if (__any_sync(0xffffffffu, m != 0u)) {
-                            NPS_DEV(const long long s0 = prof_on ? clock64() : 0;)
-                            const uint32_t code = lane | ((g - g_begin) << 13);   // + column-in-group << 8
-                            if (m & 1u) stage_hits8<0>(v, code, wcnt, hits);
-                            if (m & 2u) stage_hits8<8>(v, code, wcnt, hits);
-                            if (m & 4u) stage_hits8<16>(v, code, wcnt, hits);
-                            if (m & 8u) stage_hits8<24>(v, code, wcnt, hits);
-                            __syncwarp();
-                            NPS_DEV(if (prof_on) {
-                                prof_slow += clock64() - s0;
-                                ++prof_nslow;
-                            })
-                        }
-                    };
-                    uint32_t va[32], vb[32];
-                    uint32_t g = g_begin;
-                    if (g < g_end) {
-                        tmem_ld32(t_addr + g * 32u, va);
-                        tmem_ld_wait();
+                        for (int j = 2; j < 8; j += 2) acc &= v[8 * qd + j] & v[8 * qd + j + 1];
+                        m |= (acc >> 31 ^ 1u) << qd;
                     }
-                    while (g < g_end) {
-                        if (g + 1 < g_end) tmem_ld32(t_addr + (g + 1) * 32u, vb);
-                        const uint32_t any_a = test(va);
-                        if (g + 1 < g_end) tmem_ld_wait();
-                        slow(va, any_a, g);
-                        if (g + 1 >= g_end) break;
-                        if (g + 2 < g_end) tmem_ld32(t_addr + (g + 2) * 32u, va);
-                        const uint32_t any_b = test(vb);
-                        if (g + 2 < g_end) tmem_ld_wait();
-                        slow(vb, any_b, g + 1);
-                        g += 2;
-                    }
-                    // staging overflow (loose early-phase thresholds): redo this warp's columns exactly
-                    if (*reinterpret_cast<volatile uint32_t*>(wcnt) > (uint32_t)kMmaHitsPerWarp) {
-                        for (uint32_t gg = g_begin; gg < g_end; ++gg)
-                            rescan_group(t_addr + gg * 32u, thr_s + (gg - g_begin) * 32u, q0 + gg * 32u, grow, bits, valid,
-                                         p.cnt, p.cand, p.cap);
-                        __syncwarp();
-                        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(wcnt) = 0;
-                        __syncwarp();
+                    m = (valid && !(p.debug & 1u)) ? (m & qmask) : 0u;
+                    const uint32_t wm = __reduce_or_sync(0xffffffffu, m);   // quarters with a survivor in any lane
+                    if (wm) {
+                        NPS_DEV(const long long s0 = prof_on ? clock64() : 0;)
+                        uint32_t wn = 0;   // survivors staged for this tile (warp-uniform)
+                        if (wm & 1u) stage_hits8<0>(v, (m & 1u) != 0u, lane, wn, hits, lane_lt);
+                        if (wm & 2u) stage_hits8<8>(v, (m & 2u) != 0u, lane, wn, hits, lane_lt);
+                        if (wm & 4u) stage_hits8<16>(v, (m & 4u) != 0u, lane, wn, hits, lane_lt);
+                        if (wm & 8u) stage_hits8<24>(v, (m & 8u) != 0u, lane, wn, hits, lane_lt);
+                        if (wm & 16u) stage_hits8<32>(v, (m & 16u) != 0u, lane, wn, hits, lane_lt);
+                        if (wm & 32u) stage_hits8<40>(v, (m & 32u) != 0u, lane, wn, hits, lane_lt);
+                        if (wm & 64u) stage_hits8<48>(v, (m & 64u) != 0u, lane, wn, hits, lane_lt);
+                        // staging overflow (loose early-phase thresholds): redo this warp's columns exactly
+                        if (wn > (uint32_t)kMmaHitsPerWarp) {
+                            rescan_group(t_addr, thr_s, q0, (int)min(cpw, 32u), grow, bits, valid, p.cnt, p.cand, p.cap);
+                            if (cpw > 32u)
+                                rescan_group(t_addr + 32u, thr_s + 32, q0 + 32u, (int)(cpw - 32u), grow, bits, valid, p.cnt,
+                                             p.cand, p.cap);
+                            wn = 0;
+                        }
+                        staged = wn;
+                        NPS_DEV(if (prof_on) {
+                            prof_slow += clock64() - s0;
+                            ++prof_nslow;
+                        })
                     }
                 }
                 tc_fence_before();
@@ -537,7 +526,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 NPS_DEV(const long long pc2 = prof_on ? clock64() : 0; prof_tile += pc2 - pc1;)
                 if (ew == 0 && lane == 0) NPS_TRACE(2, 2);   // accumulator released
-                // Flush this warp's hit buffer, one entry per lane.  The atomic that reserves the
+                // Flush this warp's staging buffer, one entry per lane.  The atomic that reserves the
                 // slot is issued now, the dependent store one tile later (pend_*), so the ~1 us
                 // round trip of the returning atomic is never waited for.
                 if constexpr (!kDense) {
@@ -546,15 +535,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                         if (pend_pos < p.cap) p.cand[(size_t)pend_q * p.cap + pend_pos] = pend_key;
                         pend_q = 0xFFFFFFFFu;
                     }
-                    const uint32_t n = *reinterpret_cast<volatile uint32_t*>(wcnt);   // <= kMmaHitsPerWarp here
+                    const uint32_t n = staged;   // <= kMmaHitsPerWarp
                     if (n) {
+                        __syncwarp();
                         // decode a staged entry: (dot - T, lane | column << 8) -> (query, key)
                         auto decode = [&](uint32_t e, uint32_t& q, uint64_t& key) {
                             const uint2 h = hits[e];
-                            const uint32_t col = h.y >> 8;   // column within this warp's groups
+                            const uint32_t col = h.y >> 8;   // column within this warp's part
                             const int dot = (int)(__uint_as_float(h.x) + thr_s[col]);
                             const uint64_t r = grow - lane + (h.y & 31u);
-                            q = q0 + g_begin * 32u + col;
+                            q = q0 + col;
                             key = ((uint64_t)((bits - dot) >> 1) << kGlobalRowBits) | r;
                         };
                         for (uint32_t e = lane + 32u; e < n; e += 32u) {   // rare: more than 32 staged entries
@@ -568,15 +558,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                             pend_pos = atomicAdd(p.cnt + pend_q, 1u);
                         }
                         __syncwarp();
-                        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(wcnt) = 0;
-                        __syncwarp();
                     }
                     NPS_DEV(if (prof_on) prof_flush += clock64() - f0;)
                 }
             }
         }
         if (pend_q != 0xFFFFFFFFu && pend_pos < p.cap) p.cand[(size_t)pend_q * p.cap + pend_pos] = pend_key;
-        NPS_DEV(if (prof_on && lane == 0) {   // role slot 3 is shared with issuer 1: use its tail
+        NPS_DEV(if (prof_on && lane == 0 && ew < 8) {   // role slot 3 is shared with issuer 1: use its tail
             unsigned long long* o = p.trace + (3u * 4096u + 4000u + ew * 8u) * 2u;
             o[0] = (unsigned long long)prof_wait;
             o[1] = (unsigned long long)prof_tile;
@@ -861,7 +849,8 @@ cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned 
             sp.ring_per_issuer = pl.ring_per_issuer;
             sp.trace = nullptr;
             const char* trace_path = getenv("NPS_MMA_TRACE");
-            if (trace_path && last) {
+            const char* trace_phase = getenv("NPS_MMA_TRACE_PHASE");
+            if (trace_path && (trace_phase ? (uint32_t)atoi(trace_phase) == ph : last)) {
                 cudaMalloc(&sp.trace, 4 * 4096 * 16);
                 cudaMemsetAsync(sp.trace, 0, 4 * 4096 * 16, stream);
             }

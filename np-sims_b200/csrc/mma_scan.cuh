@@ -33,10 +33,10 @@ namespace nps {
 #define NPS_MMA_EXP_WARPS 8
 #endif
 #ifndef NPS_MMA_EPI_WARPS
-#define NPS_MMA_EPI_WARPS 8
+#define NPS_MMA_EPI_WARPS 16
 #endif
 constexpr int kMmaExpWarps = NPS_MMA_EXP_WARPS;   // 4 or 8: threads per operand row = kMmaExpWarps / 4
-constexpr int kMmaEpiWarps = NPS_MMA_EPI_WARPS;   // 4 or 8
+constexpr int kMmaEpiWarps = NPS_MMA_EPI_WARPS;   // 16: 4 TMEM lane quarters x 4 column parts
 constexpr int kMmaThreads = (4 + kMmaExpWarps + kMmaEpiWarps) * 32;   // + producer + 2 MMA issuers + 1 idle (full warpgroup)
 constexpr int kMmaTileRows = 128;         // UMMA M
 constexpr int kMmaKBlockBytes = 128;      // one swizzle row = 256 E2M1 = 256 signature bits = 4 words
@@ -92,7 +92,7 @@ __host__ __device__ inline MmaSmem mma_smem_layout(uint32_t words, uint32_t n_ti
     off += kMmaEpiWarps * (kMmaHitsPerWarp + 1) * 8;   // (accumulator bits, position code) + 1 overflow slot
     s.hitq_off = off;
     s.thr_off = off;   // per epilogue warp: thresholds of its column groups
-    off += kMmaEpiWarps * (kMmaMaxNTile / 32u / (kMmaEpiWarps / 4) + 1u) * 32u * 4u;
+    off += kMmaEpiWarps * 64u * 4u;
     s.wcnt_off = off;
     off += kMmaEpiWarps * 4;
     off = (off + 7u) & ~7u;

@@ -117,6 +117,37 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// this warp's 32 lanes x 64 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+                 : "r"(taddr)
+                 : "memory");
+}
+// this warp's 32 lanes x 32 consecutive 32-bit columns into v[O .. O+32)
+template <int O, int LEN>
+__device__ __forceinline__ void tmem_ld32_at(uint32_t taddr, uint32_t (&v)[LEN]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[O + 0]), "=r"(v[O + 1]), "=r"(v[O + 2]), "=r"(v[O + 3]), "=r"(v[O + 4]), "=r"(v[O + 5]), "=r"(v[O + 6]), "=r"(v[O + 7]), "=r"(v[O + 8]), "=r"(v[O + 9]), "=r"(v[O + 10]), "=r"(v[O + 11]), "=r"(v[O + 12]), "=r"(v[O + 13]), "=r"(v[O + 14]), "=r"(v[O + 15]), "=r"(v[O + 16]), "=r"(v[O + 17]), "=r"(v[O + 18]), "=r"(v[O + 19]), "=r"(v[O + 20]), "=r"(v[O + 21]), "=r"(v[O + 22]), "=r"(v[O + 23]), "=r"(v[O + 24]), "=r"(v[O + 25]), "=r"(v[O + 26]), "=r"(v[O + 27]), "=r"(v[O + 28]), "=r"(v[O + 29]), "=r"(v[O + 30]), "=r"(v[O + 31])
+                 : "r"(taddr)
+                 : "memory");
+}
+// this warp's 32 lanes x 16 consecutive 32-bit columns into v[O .. O+16)
+template <int O, int LEN>
+__device__ __forceinline__ void tmem_ld16_at(uint32_t taddr, uint32_t (&v)[LEN]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[O + 0]), "=r"(v[O + 1]), "=r"(v[O + 2]), "=r"(v[O + 3]), "=r"(v[O + 4]), "=r"(v[O + 5]), "=r"(v[O + 6]), "=r"(v[O + 7]), "=r"(v[O + 8]), "=r"(v[O + 9]), "=r"(v[O + 10]), "=r"(v[O + 11]), "=r"(v[O + 12]), "=r"(v[O + 13]), "=r"(v[O + 14]), "=r"(v[O + 15])
+                 : "r"(taddr)
+                 : "memory");
+}
+// this warp's 32 lanes x 8 consecutive 32-bit columns into v[O .. O+8)
+template <int O, int LEN>
+__device__ __forceinline__ void tmem_ld8_at(uint32_t taddr, uint32_t (&v)[LEN]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[O + 0]), "=r"(v[O + 1]), "=r"(v[O + 2]), "=r"(v[O + 3]), "=r"(v[O + 4]), "=r"(v[O + 5]), "=r"(v[O + 6]), "=r"(v[O + 7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
