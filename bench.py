@@ -310,36 +310,75 @@ def run_b200(args, wl):
 
     # ---- roofline pass: the dominant kernel timed per launch on its stream
     _lib.raw("nps_profile_enable")(1)
-    scan_ms, merge_ms = [], []
+    scan_ms, merge_ms, phase_runs = [], [], []
     for i in range(max(3, min(args.steps, 10))):
         flush.fill_(i)
         step_device()
         s_ms, m_ms = _lib.profile_last()
         scan_ms.append(s_ms)
         merge_ms.append(m_ms)
+        if _lib.raw("nps_last_scan_path")() == _lib.SCAN_MMA:
+            phase_runs.append(_lib.profile_last_phases())
     _lib.raw("nps_profile_enable")(0)
-    plan = _lib.last_scan_plan()
     scan_avg = float(np.mean(scan_ms))
     n_local = b[rank + 1] - b[rank]
-    # algorithmic bytes of one scan launch: signatures + queries + results
-    alg_bytes = n_local * words * 8 + nq * words * 8 + nq * plan["num_chunks"] * k * 8
-    achieved_gbs = alg_bytes / (scan_avg * 1e-3) / 1e9
-    popc32 = 2.0 * n_local * nq * words
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max_mhz
-    popc_peak = 148 * 16 * sm_mhz * 1e6
-    roofline = {
-        "kernel": f"scan_topk_kernel<W={words},R={plan['rows_per_thread']}>",
-        "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-        "ms_per_launch": scan_avg, "share_of_step": scan_avg / (total_ms / args.steps),
-        "note": ("at this batch size the scan re-reads an L2-resident table once per query tile and is bound "
-                 "by the integer POPC pipe, not HBM; see `popc` for that roofline and `roofline_stream` for "
-                 "the HBM-bound single-query scan"),
-        "popc": {"achieved_gpopc32_s": popc32 / (scan_avg * 1e-3) / 1e9,
-                 "peak_gpopc32_s": popc_peak / 1e9, "frac": popc32 / (scan_avg * 1e-3) / popc_peak,
-                 "peak_formula": f"148 SM x 16 POPC/clk x {sm_mhz:.0f} MHz (median clock under load)"},
-        "plan": plan, "merge_ms_per_launch": float(np.mean(merge_ms)),
-    }
+    step_ms = total_ms / args.steps
+    if phase_runs:
+        # Tensor-core scan (mma_scan_kernel): bound by the tensor pipe.  Algorithmic work of a launch
+        # = 2 * rows * queries * bits flop (one +-1 multiply-add per signature bit and (row, query)
+        # pair; the folded-threshold slice is overhead, not counted).  Peak: kind::mxf4 runs at 4x
+        # the bf16 rate (9 vs 2.25 PFLOP/s nominal); MEASURED_PEAKS.json holds the bf16 figure.
+        plan = _lib.last_mma_plan()
+        bf16_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] \
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
+        tensor_peak = 4.0 * bf16_peak
+        nph = len(phase_runs[0])
+        tiles = [phase_runs[0][j][0] for j in range(nph)]
+        ph_ms = [float(np.mean([r[j][1] for r in phase_runs])) for j in range(nph)]
+        dom = int(np.argmax(ph_ms))
+        rows_dom = min(tiles[dom] * 128, n_local)
+        flop_dom = 2.0 * rows_dom * nq * wl["bits"]
+        ach = flop_dom / (ph_ms[dom] * 1e-3) / 1e12
+        flop_all = 2.0 * n_local * nq * wl["bits"]
+        roofline = {
+            "kernel": f"mma_scan_kernel<dense=false> (tcgen05 kind::mxf4, M128 x N{plan['n_tile']} x K64), phase {dom} of {nph}",
+            "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
+            "traffic": None,
+            "peak_source": "4 x measured bf16 burst (MEASURED_PEAKS.json): mxf4 : bf16 = 9 : 2.25 PFLOP/s nominal; "
+                           "scripts/ubench/umma_mxf4_probe measured 16359 MAC/clk/SM issue rate in-kernel",
+            "ms_per_launch": ph_ms[dom], "share_of_step": ph_ms[dom] / step_ms,
+            "algorithmic": {"rows": rows_dom, "queries": nq, "bits": wl["bits"], "flop": flop_dom},
+            "phases": [{"tiles": t, "scan_ms": m} for t, m in zip(tiles, ph_ms)],
+            "all_phases": {"scan_ms": float(np.sum(ph_ms)), "scan_plus_select_ms": scan_avg,
+                           "achieved_tflops": flop_all / (scan_avg * 1e-3) / 1e12,
+                           "frac": flop_all / (scan_avg * 1e-3) / 1e12 / tensor_peak},
+            "plan": plan,
+            "popc_equivalent": {"gpopc32_s": 2.0 * n_local * nq * words / (scan_avg * 1e-3) / 1e9,
+                                "popc_pipe_peak_gpopc32_s": 148 * 16 * sm_mhz * 1e6 / 1e9,
+                                "note": "the XOR+POPC formulation of the same batch would need this POPC rate; "
+                                        "the integer pipe peaks at 148 SM x 16 /clk"},
+        }
+    else:
+        plan = _lib.last_scan_plan()
+        # algorithmic bytes of one scan launch: signatures + queries + results
+        alg_bytes = n_local * words * 8 + nq * words * 8 + nq * plan["num_chunks"] * k * 8
+        achieved_gbs = alg_bytes / (scan_avg * 1e-3) / 1e9
+        popc32 = 2.0 * n_local * nq * words
+        popc_peak = 148 * 16 * sm_mhz * 1e6
+        roofline = {
+            "kernel": f"scan_topk_kernel<W={words},R={plan['rows_per_thread']}>",
+            "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+            "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "ms_per_launch": scan_avg, "share_of_step": scan_avg / step_ms,
+            "note": ("at this batch size the scan re-reads an L2-resident table once per query tile and is bound "
+                     "by the integer POPC pipe, not HBM; see `popc` for that roofline and `roofline_stream` for "
+                     "the HBM-bound single-query scan"),
+            "popc": {"achieved_gpopc32_s": popc32 / (scan_avg * 1e-3) / 1e9,
+                     "peak_gpopc32_s": popc_peak / 1e9, "frac": popc32 / (scan_avg * 1e-3) / popc_peak,
+                     "peak_formula": f"148 SM x 16 POPC/clk x {sm_mhz:.0f} MHz (median clock under load)"},
+            "plan": plan, "merge_ms_per_launch": float(np.mean(merge_ms)),
+        }
 
     line = None
     if rank == 0:
@@ -365,7 +404,7 @@ def run_b200(args, wl):
             "data": "synthetic",
             "config": {"workload": wl["desc"], "rows": wl["rows"], "bits": wl["bits"], "queries": nq, "k": k,
                        "parallelism": f"row-sharded x{world}" + (" + NCCL all-gather of candidate keys" if world > 1 else ""),
-                       "step": "hash query batch (K1) + fused scan/top-n (K2) + merge (K3)" + ("+K4" if world > 1 else ""),
+                       "step": "hash query batch (K1) + batched scan/top-n (K2T tensor-core phases + select)" + (" + all-gather + K4 merge" if world > 1 else ""),
                        "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)",
                        "index_build_s": index_s},
             "clocks": clocks,

@@ -77,6 +77,9 @@ typedef struct nps_mma_plan {
         last_tiles_per_chunk, last_num_chunks, last_grid, reserved;
 } nps_mma_plan_t;
 int nps_last_mma_plan(nps_mma_plan_t *out);
+/* After a profiled call that took the tensor-core path: device duration of each phase's scan
+ * launch and the number of 128-row tiles it covered (phase 0 = dense bootstrap). */
+int nps_profile_last_phases(float *scan_ms, uint32_t *tiles, uint32_t max_phases, uint32_t *num_phases);
 /* Tensor-core path only: number of queries whose candidate buffer overflowed during the call
  * that used d_workspace (0 in all but adversarial inputs).  Synchronises the stream.  A caller
  * that sees a non-zero count repeats the call with NPS_SCAN_POPC (the host-level entry points

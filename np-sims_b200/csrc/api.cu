@@ -68,10 +68,13 @@ static int g_scan_path = NPS_SCAN_AUTO;     // nps_set_scan_path
 static int g_last_path = NPS_SCAN_POPC;     // which kernel family the last top-n call used
 static MmaPlan g_last_mma_plan = {};
 static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
+static cudaEvent_t g_phase_ev[2 * kMmaMaxPhases] = {};   // tensor-core path: one pair per phase
 static ScanPlanInfo g_last_plan = {};
 
 static int profile_events() {
     for (auto& e : g_ev)
+        if (!e) NPS_CUDA(cudaEventCreate(&e));
+    for (auto& e : g_phase_ev)
         if (!e) NPS_CUDA(cudaEventCreate(&e));
     return NPS_OK;
 }
@@ -214,10 +217,14 @@ static int run_top_n(const uint64_t* d_hashes, uint64_t N, uint32_t W, const uin
         if (g_profile) {
             rc = profile_events();
             if (rc) return rc;
+            NPS_CUDA(cudaEventRecord(g_ev[0], stream));
         }
         NPS_CUDA(run_mma_top_n(mp, d_hashes, N, W, d_queries, Q, k, row_base, d_rows, d_dists, d_keys_out, ws, stream,
-                               g_profile ? g_ev[0] : nullptr, g_profile ? g_ev[1] : nullptr));
-        if (g_profile) NPS_CUDA(cudaEventRecord(g_ev[2], stream));
+                               g_profile ? g_phase_ev : nullptr));
+        if (g_profile) {
+            NPS_CUDA(cudaEventRecord(g_ev[1], stream));   // scan = all phases (scan + select launches)
+            NPS_CUDA(cudaEventRecord(g_ev[2], stream));
+        }
         return NPS_OK;
     }
     g_last_path = NPS_SCAN_POPC;
@@ -312,6 +319,21 @@ int nps_last_mma_plan(nps_mma_plan_t* out) {
     const MmaPhase& L = m.phase[m.num_phases ? m.num_phases - 1 : 0];
     *out = nps_mma_plan_t{m.n_tile, m.num_qtiles, m.cap, m.growth, m.a_stages, m.smem, m.num_phases,
                           L.tiles, L.tiles_per_chunk, L.num_chunks, L.grid, 0};
+    return NPS_OK;
+}
+
+int nps_profile_last_phases(float* scan_ms, uint32_t* tiles, uint32_t max_phases, uint32_t* num_phases) {
+    if (!scan_ms || !tiles || !num_phases) return fail(NPS_EINVAL, "null pointer");
+    if (g_last_path != NPS_SCAN_MMA || !g_phase_ev[0]) return fail(NPS_EINVAL, "no profiled tensor-core call yet");
+    const MmaPlan& m = g_last_mma_plan;
+    NPS_CUDA(cudaEventSynchronize(g_ev[2]));
+    uint32_t n = 0;
+    for (uint32_t ph = 0; ph < m.num_phases && n < max_phases; ++ph, ++n) {
+        tiles[n] = m.phase[ph].tiles;
+        scan_ms[n] = 0.f;
+        if (m.phase[ph].tiles) NPS_CUDA(cudaEventElapsedTime(&scan_ms[n], g_phase_ev[2 * ph], g_phase_ev[2 * ph + 1]));
+    }
+    *num_phases = n;
     return NPS_OK;
 }
 

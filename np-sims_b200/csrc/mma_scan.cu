@@ -807,7 +807,7 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
 cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned long long N, uint32_t W,
                           const uint64_t* d_queries, uint32_t Q, uint32_t k, unsigned long long row_base,
                           uint64_t* d_rows, uint64_t* d_dists, uint64_t* d_keys, void* ws, cudaStream_t stream,
-                          cudaEvent_t ev_scan_begin, cudaEvent_t ev_scan_end) {
+                          cudaEvent_t* phase_events) {
     uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
     uint32_t* flag = reinterpret_cast<uint32_t*>(w8 + pl.off_flag);
     uint32_t* cnt = reinterpret_cast<uint32_t*>(w8 + pl.off_cnt);
@@ -858,14 +858,14 @@ cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned 
                 const char* dbg = getenv("NPS_MMA_DEBUG");
                 sp.debug = (dbg && !sp.dense) ? (uint32_t)atoi(dbg) : 0u;
             }
-            if (last && ev_scan_begin) {
-                e = cudaEventRecord(ev_scan_begin, stream);
+            if (phase_events) {
+                e = cudaEventRecord(phase_events[2 * ph], stream);
                 if (e != cudaSuccess) return e;
             }
             e = launch_mma_scan(sp, (int)P.grid, pl.smem, stream);
             if (e != cudaSuccess) return e;
-            if (last && ev_scan_end) {
-                e = cudaEventRecord(ev_scan_end, stream);
+            if (phase_events) {
+                e = cudaEventRecord(phase_events[2 * ph + 1], stream);
                 if (e != cudaSuccess) return e;
             }
             if (sp.trace) {

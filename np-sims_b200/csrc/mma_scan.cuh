@@ -141,6 +141,6 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
 cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned long long N, uint32_t W,
                           const uint64_t* d_queries, uint32_t Q, uint32_t k, unsigned long long row_base,
                           uint64_t* d_rows, uint64_t* d_dists, uint64_t* d_keys, void* ws, cudaStream_t stream,
-                          cudaEvent_t ev_scan_begin, cudaEvent_t ev_scan_end);
+                          cudaEvent_t* phase_events);   // nullable: 2 events per phase, recorded around each scan launch
 
 }  // namespace nps

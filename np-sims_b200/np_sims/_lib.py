@@ -38,6 +38,7 @@ _SIGS = {
     "nps_set_scan_path": (_int, [_int]),
     "nps_last_scan_path": (_int, []),
     "nps_last_mma_plan": (_int, [_vp]),
+    "nps_profile_last_phases": (_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_u32), _u32, ctypes.POINTER(_u32)]),
     "nps_top_n_overflow_count": (_int, [_vp, _vp, ctypes.POINTER(ctypes.c_uint32)]),
     "nps_host_hamming_top_k": (_int, [_vp, _vp, _u64, _u64, _u32, _vp]),
     "nps_host_hamming": (_int, [_vp, _vp, _u64, _u64, _vp]),
@@ -89,6 +90,15 @@ def last_mma_plan() -> dict:
 
 
 _scan_path = SCAN_AUTO
+
+
+def profile_last_phases():
+    """[(tiles, scan_ms)] per phase of the last profiled tensor-core call."""
+    ms = (ctypes.c_float * 32)()
+    tiles = (_u32 * 32)()
+    n = _u32(0)
+    check(_lib.nps_profile_last_phases(ms, tiles, 32, ctypes.byref(n)))
+    return [(int(tiles[i]), float(ms[i])) for i in range(n.value)]
 
 
 def set_scan_path(path: int) -> int:

@@ -1,0 +1,136 @@
+"""GPU parity tests of the tensor-core batched scan (K2T, np-sims_b200/csrc/mma_scan.cu).
+
+The tcgen05 kind::mxf4 path must return bit-identical ids and distances to the oracle's canonical
+order (ascending (distance, row id)) and to the XOR+POPC scan on the same inputs: every width up
+to 23 words, ragged row/query counts, heavy ties, duplicate rows, sorted ("adversarial") row
+orders that overflow the candidate buffers, k from 1 to 1000, shard offsets."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nps():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import np_sims
+    return np_sims
+
+
+@pytest.fixture()
+def force_mma():
+    from np_sims import _lib
+    prev = _lib.set_scan_path(_lib.SCAN_MMA)
+    yield _lib
+    _lib.set_scan_path(prev)
+
+
+def rand_sigs(rng, n, w, live_bits=None):
+    h = rng.integers(0, 2**64, size=(n, w), dtype=np.uint64)
+    if live_bits is not None and live_bits < 64 * w:
+        mask = np.zeros(w, dtype=np.uint64)
+        for b in rng.choice(64 * w, size=live_bits, replace=False):
+            mask[b // 64] |= np.uint64(1) << np.uint64(b % 64)
+        h &= mask
+    return h
+
+
+def check_against_oracle(nps, h, q, k, queries):
+    rows, dists = nps.hamming_top_n(h, q, k, return_distances=True)
+    assert rows.shape == (len(q), k) and rows.dtype == np.uint64
+    for i in queries:
+        want_r, want_d = oracle.top_k_canonical(h, q[i], k)
+        assert np.array_equal(rows[i], want_r), (i, rows[i][:12], want_r[:12])
+        assert np.array_equal(dists[i], want_d), i
+    return rows, dists
+
+
+@pytest.mark.parametrize("w", [1, 2, 3, 4, 5, 7, 8, 9, 10, 12, 13, 16, 17, 20, 23])
+def test_mma_all_widths_vs_oracle(nps, force_mma, w):
+    rng = np.random.default_rng(100 + w)
+    n = int(rng.integers(3000, 20000))
+    nq = int(rng.integers(64, 300))
+    h = rand_sigs(rng, n, w)
+    q = rand_sigs(rng, nq, w)
+    q[: nq // 2] = h[rng.integers(0, n, size=nq // 2)]          # planted exact matches
+    q[: nq // 4, 0] ^= np.uint64(0b1011)
+    check_against_oracle(nps, h, q, 10, rng.choice(nq, size=10, replace=False))
+    assert force_mma.raw("nps_last_scan_path")() == force_mma.SCAN_MMA
+
+
+@pytest.mark.parametrize("n,nq", [(1, 64), (127, 65), (128, 64), (129, 100), (511, 64), (513, 223), (4097, 225),
+                                  (70001, 449)])
+def test_mma_ragged_shapes(nps, force_mma, n, nq):
+    rng = np.random.default_rng(n * 7 + nq)
+    h = rand_sigs(rng, n, 10, live_bits=40)                      # heavy ties
+    q = rand_sigs(rng, nq, 10, live_bits=40)
+    for k in (1, 10, 100):
+        check_against_oracle(nps, h, q, k, rng.choice(nq, size=6, replace=False))
+
+
+@pytest.mark.parametrize("k", [1, 2, 10, 33, 100, 257, 1000])
+def test_mma_k_values(nps, force_mma, k):
+    rng = np.random.default_rng(k)
+    h = rand_sigs(rng, 30011, 5)
+    q = rand_sigs(rng, 96, 5)
+    check_against_oracle(nps, h, q, k, [0, 17, 95])
+
+
+def test_mma_equals_popc_scan_bitwise(nps, force_mma):
+    import torch
+    rng = np.random.default_rng(5)
+    h = rand_sigs(rng, 120_000, 16)
+    q = rand_sigs(rng, 700, 16)
+    q[:300] = h[rng.integers(0, len(h), size=300)]
+    H, Q = torch.from_numpy(h.view(np.int64)).cuda(), torch.from_numpy(q.view(np.int64)).cuda()
+    r1, d1 = nps.hamming_top_n(H, Q, 100, return_distances=True)
+    force_mma.set_scan_path(force_mma.SCAN_POPC)
+    r0, d0 = nps.hamming_top_n(H, Q, 100, return_distances=True)
+    assert force_mma.raw("nps_last_scan_path")() == force_mma.SCAN_POPC
+    assert torch.equal(r0, r1) and torch.equal(d0, d1)
+
+
+def test_mma_duplicates_and_index_ties(nps, force_mma):
+    rng = np.random.default_rng(9)
+    h = np.repeat(rand_sigs(rng, 40, 3), 300, axis=0)            # 12000 rows, each signature 300 times
+    q = rand_sigs(rng, 64, 3)
+    q[:32] = h[rng.integers(0, len(h), size=32)]
+    check_against_oracle(nps, h, q, 10, range(0, 64, 7))
+    h[:] = 7                                                      # all rows identical: pure index order
+    rows = nps.hamming_top_n(h, q, 10)
+    assert rows[5].tolist() == list(range(10))
+
+
+def test_mma_sorted_rows_overflow_falls_back_exactly(nps, force_mma):
+    # Rows sorted so that every later row is CLOSER to the queries than all earlier ones: the
+    # thresholds learnt from early phases never filter anything, the candidate buffers overflow and
+    # the Python layer must redo the call on the XOR+POPC scan.  Results stay exact.
+    n, w = 40000, 4
+    rng = np.random.default_rng(3)
+    base = rand_sigs(rng, 1, w)[0]
+    h = np.tile(base, (n, 1))
+    flips = np.linspace(250, 0, n).astype(np.int64)               # distance to `base` decreases with the row id
+    order = rng.permutation(64 * w)
+    for i in range(n):
+        for b in order[: flips[i]]:
+            h[i, b // 64] ^= np.uint64(1) << np.uint64(b % 64)
+    q = np.tile(base, (64, 1))
+    rows, dists = check_against_oracle(nps, h, q, 10, [0, 63])
+    assert dists[0][0] == 0
+
+
+def test_mma_row_base_and_keys(nps, force_mma):
+    import torch
+    from np_sims.sharded import ShardedIndex
+    rng = np.random.default_rng(21)
+    h = rand_sigs(rng, 50_000, 10)
+    q = rand_sigs(rng, 128, 10)
+    whole = nps.hamming_top_n(h, q, 10)
+    parts = [ShardedIndex.from_global(h, r, 3) for r in range(3)]
+    keys = [p._keys_fn(p.hashes, torch.from_numpy(q.view(np.int64)).cuda(), 10, p.row_base) for p in parts]
+    from np_sims.sharded import _cuda_merge
+    rows, _ = _cuda_merge(torch.stack(keys), 10)
+    assert np.array_equal(rows.cpu().numpy().view(np.uint64), whole)
