@@ -43,11 +43,6 @@ extern "C" {
 #define NPS_ORDER_REFERENCE 1  /* the reference queue's slot order and tie survivors, bit-exact
                                   with ufunc.c:150-195 */
 
-/* projection arithmetic of nps_project_sign_pack */
-#define NPS_PROJ_TF32X3 0      /* 3xTF32 split on tcgen05: fp32-level accuracy */
-#define NPS_PROJ_TF32 1        /* single TF32 pass: fastest, |x.w| tolerance ~1e-3 |x||w| */
-#define NPS_PROJ_FP32_SIMT 2   /* CUDA-core fp32 FMA reference kernel (validation) */
-
 int nps_version(void);
 const char *nps_last_error(void);
 /* number of CUDA devices visible, or NPS_ECUDA */
@@ -177,6 +172,24 @@ int nps_num_unshared_bits(const uint64_t *d_a, uint64_t len_a, const uint64_t *d
 int nps_project_sign_pack_f64(const void *d_vectors, int vectors_are_f32, uint64_t num_vectors,
                               uint32_t dims, const double *d_projections, uint32_t num_projections,
                               uint64_t *d_out, double *d_dots, void *stream);
+
+/* K1T — the same hashing for float32 vectors on the tensor cores: TMA-fed tcgen05 kind::tf32
+ * GEMM with a sign/bit-pack epilogue.  Accumulators with |acc| < (2^-9 + dims * 2^-22) * |x_i| *
+ * projection_norm_max cannot be trusted at TF32 precision; those (row, projection) pairs (a few
+ * percent) are recomputed in float64 by a fix-up kernel, so the signatures equal those of
+ * nps_project_sign_pack_f64.  Needs dims % 4 == 0 and 16-byte aligned inputs.
+ * d_projections_f32 / _f64: the same [num_projections, dims] matrix in both precisions;
+ * projection_norm_max = max_j |projections[j]| (1.0 for lsh.create_projections).
+ * nps_project_sign_pack_stats (synchronises the stream) returns how many pairs were recomputed
+ * and the fix-up list capacity; recomputed > capacity means entries were dropped and the caller
+ * must redo the call with nps_project_sign_pack_f64 (the Python layer does). */
+size_t nps_project_sign_pack_workspace_bytes(uint64_t num_vectors, uint32_t num_projections);
+int nps_project_sign_pack(const float *d_vectors, uint64_t num_vectors, uint32_t dims,
+                          const float *d_projections_f32, const double *d_projections_f64,
+                          uint32_t num_projections, float projection_norm_max, uint64_t *d_out,
+                          void *d_workspace, size_t workspace_bytes, void *stream);
+int nps_project_sign_pack_stats(const void *d_workspace, uint64_t num_vectors, uint32_t num_projections,
+                                void *stream, uint32_t *recomputed, uint32_t *capacity);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

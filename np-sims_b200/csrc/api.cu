@@ -474,6 +474,48 @@ int nps_project_sign_pack_f64(const void* d_vectors, int vectors_are_f32, uint64
     return NPS_OK;
 }
 
+size_t nps_project_sign_pack_workspace_bytes(uint64_t num_vectors, uint32_t num_projections) {
+    return project_tc_workspace_bytes(num_vectors, num_projections, nullptr);
+}
+
+int nps_project_sign_pack(const float* d_vectors, uint64_t num_vectors, uint32_t dims, const float* d_projections_f32,
+                          const double* d_projections_f64, uint32_t num_projections, float projection_norm_max,
+                          uint64_t* d_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (num_projections == 0 || num_projections % 64 != 0)
+        return fail(NPS_EINVAL, "Projections must be a multiple of 64");   // lsh.py:37-38
+    if (num_vectors == 0) return NPS_OK;
+    if (!d_vectors || !d_projections_f32 || !d_projections_f64 || !d_out || !d_workspace) return fail(NPS_EINVAL, "null pointer");
+    if (!project_tc_applicable(num_vectors, dims, num_projections))
+        return fail(NPS_EINVAL, "tensor-core projection needs float32 vectors with dims %% 4 == 0 (dims=%u); use "
+                                "nps_project_sign_pack_f64", dims);
+    if ((reinterpret_cast<uintptr_t>(d_vectors) | reinterpret_cast<uintptr_t>(d_projections_f32)) & 15u)
+        return fail(NPS_EINVAL, "vectors and projections must be 16-byte aligned");
+    if (workspace_bytes < project_tc_workspace_bytes(num_vectors, num_projections, nullptr))
+        return fail(NPS_EWORKSPACE, "workspace %zu bytes < required %zu", workspace_bytes,
+                    project_tc_workspace_bytes(num_vectors, num_projections, nullptr));
+    if (!(projection_norm_max > 0.f)) return fail(NPS_EINVAL, "projection_norm_max must be > 0");
+    DeviceInfo dev;
+    int rc = device_info(&dev);
+    if (rc) return rc;
+    NPS_CUDA(launch_project_tc(d_vectors, num_vectors, dims, d_projections_f32, d_projections_f64, num_projections,
+                               projection_norm_max, d_out, d_workspace, dev.sm_count, dev.smem_optin,
+                               (cudaStream_t)stream));
+    return NPS_OK;
+}
+
+int nps_project_sign_pack_stats(const void* d_workspace, uint64_t num_vectors, uint32_t num_projections, void* stream,
+                                uint32_t* recomputed, uint32_t* capacity) {
+    if (!d_workspace || !recomputed || !capacity) return fail(NPS_EINVAL, "null pointer");
+    uint32_t cap = 0;
+    project_tc_workspace_bytes(num_vectors, num_projections, &cap);
+    const size_t off = ((size_t)num_vectors * 4 + 255) / 256 * 256;
+    NPS_CUDA(cudaMemcpyAsync(recomputed, reinterpret_cast<const uint8_t*>(d_workspace) + off, 4, cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+    NPS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *capacity = cap;
+    return NPS_OK;
+}
+
 // ------------------------------------------------------------------------------ host level
 struct nps_index {
     int device = 0;

@@ -7,4 +7,11 @@ namespace nps {
 // [n_rows, n_proj] float64 (nullable, for tolerance analysis).
 cudaError_t launch_project_f64(const void* X, int x_is_f32, unsigned long long n_rows, uint32_t dims,
                                const double* W, uint32_t n_proj, uint64_t* out, double* dots, cudaStream_t stream);
+
+// K1T: tensor-core projection (project_tc.cu).  float32 vectors only; dims % 4 == 0.
+bool project_tc_applicable(unsigned long long N, uint32_t D, uint32_t B);
+size_t project_tc_workspace_bytes(unsigned long long N, uint32_t B, uint32_t* fix_cap_out);
+cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, const float* W32, const double* W64,
+                              uint32_t B, float w_norm_max, uint64_t* out, void* ws, int sm_count, int smem_optin,
+                              cudaStream_t stream);
 }  // namespace nps

@@ -32,9 +32,11 @@ class DeviceArray(np.ndarray):
     """
 
     _nps_dev = None
+    _nps_dev32 = None
 
     def __array_finalize__(self, obj):
         self._nps_dev = None
+        self._nps_dev32 = None
 
     def __reduce__(self):  # pickle / np.save as a plain array
         return np.asarray(self).view(np.ndarray).__reduce__()

@@ -15,7 +15,6 @@ NPS_OK, NPS_EINVAL, NPS_ECUDA, NPS_EWORKSPACE = 0, -1, -2, -3
 NPS_MAX_K, NPS_MAX_WORDS = 2048, 1024
 ORDER_CANONICAL, ORDER_REFERENCE = 0, 1
 SCAN_AUTO, SCAN_POPC, SCAN_MMA = 0, 1, 2
-PROJ_TF32X3, PROJ_TF32, PROJ_FP32_SIMT = 0, 1, 2
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -55,6 +54,9 @@ _SIGS = {
     "nps_hamming_top_n_reference_workspace_bytes": (_sz, [_u64, _u32, _u32]),
     "nps_hamming_top_n_reference": (_int, [_vp, _u64, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _sz, _vp]),
     "nps_num_unshared_bits": (_int, [_vp, _u64, _vp, _u64, _u64, _vp, _vp]),
+    "nps_project_sign_pack_workspace_bytes": (_sz, [_u64, _u32]),
+    "nps_project_sign_pack": (_int, [_vp, _u64, _u32, _vp, _vp, _u32, ctypes.c_float, _vp, _vp, _sz, _vp]),
+    "nps_project_sign_pack_stats": (_int, [_vp, _u64, _u32, _vp, ctypes.POINTER(_u32), ctypes.POINTER(_u32)]),
     "nps_project_sign_pack_f64": (_int, [_vp, _int, _u64, _u32, _vp, _u32, _vp, _vp, _vp]),
 }
 for _name, (_res, _args) in _SIGS.items():

@@ -60,10 +60,36 @@ def _vectors_device(vectors):
     return t.from_numpy(arr).cuda()
 
 
-def hash_vectors(vectors, projections, return_dots=False):
+# Hashing statistics of the last tensor-core call: (row, projection) pairs whose TF32 accumulator
+# was too close to zero to trust and that were recomputed in float64 (tests / bench read this).
+last_hash_stats = {"path": None, "pairs": 0, "recomputed": 0}
+
+
+def _projections_f32(projections, P64):
+    """float32 copy of the projections and max_j |w_j| for the tensor-core pass (cached on the
+    DeviceArray next to the float64 upload)."""
+    t = require_cuda()
+    cached = getattr(projections, "_nps_dev32", None) if isinstance(projections, DeviceArray) else None
+    if cached is not None:
+        return cached
+    P32 = P64.to(t.float32).contiguous()
+    norm_max = float(t.linalg.vector_norm(P64, dim=1).max().item()) * (1.0 + 1e-6)
+    out = (P32, norm_max)
+    if isinstance(projections, DeviceArray):
+        projections._nps_dev32 = out
+    return out
+
+
+def hash_vectors(vectors, projections, return_dots=False, exact_only=False, tf32_raw=False):
     """Device-level hashing: vectors [N, D] -> int64 CUDA tensor [N, B/64] carrying the uint64
     signatures (bit j = (projections[j] . x >= 0) at word j//64, bit j%64 — lsh.py:33).
-    float64 arithmetic on the GPU (K1a).  With return_dots also the [N, B] float64 projections."""
+
+    float32 vectors with D % 4 == 0 take the tensor-core path (K1T: TMA-fed tcgen05 TF32 GEMM,
+    sign/bit-pack epilogue, float64 fix-up of the few percent of pairs whose accumulator is too
+    close to zero); everything else, `return_dots` and `exact_only` take the float64 CUDA-core
+    kernel (K1a).  Both give the signatures of the reference's float64 arithmetic.
+    `tf32_raw=True` (measurement only) disables the fix-up, returning the bare TF32 signs, so that
+    the flipped-bit rate of the tensor-core arithmetic itself can be reported."""
     t = require_cuda()
     P = _projections_device(projections)
     X = _vectors_device(vectors)
@@ -74,11 +100,27 @@ def hash_vectors(vectors, projections, return_dots=False):
     if P.shape[0] % 64 != 0:
         raise ValueError("Projections must be a multiple of 64")
     X = X.to(P.device)
-    out = t.empty((X.shape[0], P.shape[0] // 64), dtype=t.int64, device=P.device)
-    dots = t.empty((X.shape[0], P.shape[0]), dtype=t.float64, device=P.device) if return_dots else None
+    n, d, b = X.shape[0], X.shape[1], P.shape[0]
+    out = t.empty((n, b // 64), dtype=t.int64, device=P.device)
     with t.cuda.device(P.device):
-        _lib.call("nps_project_sign_pack_f64", ptr(X), int(X.dtype == t.float32), X.shape[0], X.shape[1], ptr(P),
-                  P.shape[0], ptr(out), ptr(dots), stream_ptr())
+        if (X.dtype == t.float32 and not return_dots and not exact_only and n > 0 and d % 4 == 0 and b <= 65536
+                and X.data_ptr() % 16 == 0):
+            P32, norm_max = _projections_f32(projections, P)
+            ws_bytes = _lib.raw("nps_project_sign_pack_workspace_bytes")(n, b)
+            ws = t.empty(ws_bytes, dtype=t.uint8, device=P.device)
+            _lib.call("nps_project_sign_pack", ptr(X), n, d, ptr(P32), ptr(P), b, 1e-30 if tf32_raw else norm_max,
+                      ptr(out), ptr(ws), ws_bytes, stream_ptr())
+            import ctypes
+            fixed, cap = ctypes.c_uint32(0), ctypes.c_uint32(0)
+            _lib.call("nps_project_sign_pack_stats", ptr(ws), n, b, stream_ptr(), ctypes.byref(fixed), ctypes.byref(cap))
+            last_hash_stats.update(path="tf32+fixup", pairs=n * b, recomputed=int(fixed.value))
+            if fixed.value <= cap.value:
+                return out
+            # fix-up list overflowed (degenerate input, e.g. vectors orthogonal to everything): redo exactly
+        dots = t.empty((n, b), dtype=t.float64, device=P.device) if return_dots else None
+        _lib.call("nps_project_sign_pack_f64", ptr(X), int(X.dtype == t.float32), n, d, ptr(P), b, ptr(out), ptr(dots),
+                  stream_ptr())
+        last_hash_stats.update(path="f64", pairs=n * b, recomputed=n * b)
     return (out, dots) if return_dots else out
 
 

@@ -337,3 +337,49 @@ def test_torch_tensor_inputs_stay_on_device(nps):
     got = rows.view(torch.int64).cpu().numpy().view(np.uint64)
     for i in range(4):
         assert np.array_equal(got[i], oracle.top_k_canonical(h, q[i], 10)[0])
+
+
+# ------------------------------------------------------------------------------ K1T tensor-core hashing
+@pytest.mark.parametrize("n,dims,bits", [(1, 300, 640), (127, 300, 640), (1019, 300, 640), (5000, 768, 1024),
+                                         (3001, 100, 128), (2000, 52, 64), (4096, 300, 2560)])
+def test_tensor_core_hash_equals_float64_oracle(nps, n, dims, bits):
+    """K1T (tcgen05 TF32 GEMM + float64 fix-up) must give the oracle's float64 signatures; the
+    bare TF32 signs may only differ where |x.w| is below the stated tolerance."""
+    import torch
+    import np_sims.lsh as lsh
+    rng = np.random.default_rng(n + dims)
+    X = rng.standard_normal((n, dims)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    X[: n // 7] *= rng.uniform(0.01, 50.0, size=(n // 7, 1)).astype(np.float32)      # not all unit norm
+    np.random.seed(bits)
+    W = lsh.create_projections(bits, dims)
+    want = oracle.index_np(X, np.asarray(W))
+    got = lsh.index(X, W)
+    assert lsh.last_hash_stats["path"] == "tf32+fixup"
+    assert np.array_equal(np.asarray(got), want)
+    frac = lsh.last_hash_stats["recomputed"] / lsh.last_hash_stats["pairs"]
+    assert frac < 0.12, frac
+    # bare TF32: flipped bits only where the float64 projection is inside the tolerance
+    raw = lsh.hash_vectors(torch.from_numpy(X).cuda(), W, tf32_raw=True).cpu().numpy().view(np.uint64)
+    flips = np.unpackbits((raw ^ want).view(np.uint8), bitorder="little").reshape(n, -1)[:, :bits].astype(bool)
+    dots = X.astype(np.float64) @ np.asarray(W).T
+    tol = (2.0 ** -9 + dims * 2.0 ** -22) * np.linalg.norm(X.astype(np.float64), axis=1, keepdims=True) * 1.0001
+    assert not np.any(flips & (np.abs(dots) >= tol)), "TF32 flipped a bit outside the stated tolerance"
+    print(f"K1T n={n} dims={dims} bits={bits}: raw TF32 flipped-bit rate {flips.mean():.2e}, "
+          f"recomputed in float64 {frac:.3%}")
+
+
+def test_tensor_core_hash_degenerate_inputs(nps):
+    import np_sims.lsh as lsh
+    np.random.seed(1)
+    W = lsh.create_projections(128, 64)
+    X = np.zeros((300, 64), dtype=np.float32)                   # zero vectors: dot == 0 -> every bit 1
+    X[100:200] = np.asarray(W)[5].astype(np.float32) * 0.0      # still zero
+    X[200:] = np.eye(64, dtype=np.float32)[np.arange(100) % 64] * 1e-20
+    got = lsh.index(X, W)
+    assert np.array_equal(np.asarray(got), oracle.index_np(X, np.asarray(W)))
+    # float64 vectors and dims % 4 != 0 take the float64 kernel
+    X2 = np.random.default_rng(0).standard_normal((50, 63))
+    W2 = lsh.create_projections(64, 63)
+    assert np.array_equal(np.asarray(lsh.index(X2, W2)), oracle.index_np(X2, np.asarray(W2)))
+    assert lsh.last_hash_stats["path"] == "f64"
