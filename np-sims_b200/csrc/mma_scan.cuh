@@ -6,24 +6,24 @@
 // On sm_100a the integer route costs 2 POPC per 64-bit word-pair on a 16-lane/clk/SM pipe
 // (profiles/r01_scan_topk_c2_popc.txt: XU pipe 56 % busy, DRAM 0.01 %), i.e. the batched scan is
 // compute-bound, not HBM-bound, and sm_100a has no native 1-bit MMA.  The
-// closest native tensor-core form is kind::f8f6f4 with E4M3 operands holding exactly +-1.0 and
-// FP32 accumulation in TMEM: every partial sum is an integer of magnitude <= bits < 2^24, so
-// the result is EXACT — bit-identical distances — at 8192 MAC/clk/SM instead of 8 word-pairs.
-// The signature table stays bit-packed in HBM/L2 (no 8x expansion of traffic): tiles are
-// expanded to E4M3 on chip, straight into the swizzled shared-memory operand layout.
+// closest native tensor-core form is kind::mxf4: E2M1 operands holding exactly +-1.0, unit block
+// scales, FP32 accumulation in TMEM.  Every partial sum is an integer of magnitude <= bits < 2^24,
+// so the result is EXACT — bit-identical distances — at 16384 MAC/clk/SM instead of 8 word-pairs.
+// The signature table stays bit-packed in HBM/L2 (no expansion of traffic): tiles are expanded to
+// E2M1 on chip, straight into the swizzled shared-memory operand layout.
 //
-// Kernel structure (one persistent CTA per SM, 14 warps, warp-specialised):
-//   warp 0      producer  : 1-D TMA bulk copies of bit-packed row tiles (128 rows) into a ring
-//   warp 1      MMA issuer: tcgen05.mma M=128 x N=n_tile x K=32, accumulators double-buffered in TMEM
-//   warps 2-5   expanders : bit-packed words -> E4M3 +-1 bytes, K-major SWIZZLE_128B operand tiles
-//                           (B = the query tile, once per work item; A = row tile, per K-block)
-//   warps 6-13  epilogue  : tcgen05.ld the 128 x n_tile dot products, threshold filter, append
+// Kernel structure (one persistent CTA per SM, 28 warps, warp-specialised):
+//   warps 0-15  epilogue  : one tcgen05.ld per tile and warp, sign test of  dot - threshold , staging
+//   warps 16-23 expanders : bit-packed words -> E2M1 +-1, K-major SWIZZLE_128B operand tiles
+//                           (B = the query tile, once per work item; A = row tile, per group)
+//   warp 24     producer  : 1-D TMA bulk copies of bit-packed row tiles (128 rows) into a ring
+//   warps 25-26 MMA issue : tcgen05.mma M=128 x N=n_tile x K=64, accumulators double-buffered in TMEM
 // Selection: the kernel does no top-k bookkeeping.  Each launch ("phase") filters against a
 // fixed per-query threshold (the exact k-th best key over the rows of all previous phases) and
 // appends survivors (key = dist << 40 | row) to a per-query candidate buffer; mma_select_kernel
 // then folds the candidates into the exact running top-k and tightens the threshold.  Phases
-// visit the row tiles of the table in an interleaved (strided) order, each phase ~G x larger
-// than everything before it, so the expected number of survivors per query and phase is ~k*G.
+// visit the row tiles of the table in nested strided subsets, early ones ~8x larger than
+// everything before them, the last three 2x, so few accumulator groups hold a survivor.
 #pragma once
 #include "tc.cuh"
 

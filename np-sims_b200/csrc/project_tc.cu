@@ -165,24 +165,32 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     uint32_t v[32];
                     tmem_ld32(t_addr + c0 + h * 32u, v);
                     tmem_ld_wait();
-                    uint32_t bits = 0;
-                    bool unsure = false;
+                    uint32_t bits = 0, unsure = 0;      // per column: sign, |acc| below the tolerance
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float a = __uint_as_float(v[j]);
                         bits |= (a >= 0.f ? 1u : 0u) << j;
-                        unsure |= fabsf(a) < tol;
+                        unsure |= (fabsf(a) < tol ? 1u : 0u) << j;
                     }
                     lohi[h] = bits;
-                    if (unsure) {   // rare: a few percent of the entries
+                    // Fix-up list: ONE global atomic per warp and 32-column group (a per-entry atomic on
+                    // the single counter serialised in L2: measured 5 ms for 7 M entries).
+                    const uint32_t mine = __popc(unsure);
+                    uint32_t incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += up;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total) {   // warp-uniform
+                        uint32_t basepos = 0;
+                        if (lane == 31) basepos = atomicAdd(p.fix_count, total);
+                        basepos = __shfl_sync(0xffffffffu, basepos, 31);
+                        uint32_t pos = basepos + incl - mine;
                         const uint32_t col0 = nt * NT + c0 + h * 32u;
-#pragma unroll 1
-                        for (int j = 0; j < 32; ++j) {
-                            if (fabsf(__uint_as_float(v[j])) < tol) {
-                                const unsigned int pos = atomicAdd(p.fix_count, 1u);
-                                if (pos < p.fix_cap) p.fix[pos] = (row << 16) | (unsigned long long)(col0 + j);
-                            }
-                        }
+                        for (uint32_t m = unsure; m; m &= m - 1u, ++pos)
+                            if (pos < p.fix_cap) p.fix[pos] = (row << 16) | (unsigned long long)(col0 + (__ffs(m) - 1));
                     }
                 }
                 if (valid)
