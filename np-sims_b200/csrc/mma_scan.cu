@@ -655,7 +655,89 @@ __global__ void __launch_bounds__(kSelectThreads) mma_select_kernel(const MmaSel
     }
 }
 
+// Small-k variant (k <= 32, the reference's top-10): one WARP per query, k rounds of "global minimum":
+// every lane tracks the minimum of its strided slice of the keys in shared memory, a warp min-reduce
+// picks the winner, the owning lane strikes it out and rescans its slice.  O(n + k * n / 32) instead of
+// a full sort; 8 queries per CTA instead of one.
+constexpr int kSelectWarps = 8;
+
+__global__ void __launch_bounds__(kSelectWarps * 32) mma_select_warp_kernel(const MmaSelectParams p) {
+    extern __shared__ __align__(16) uint64_t skeys[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * kSelectWarps + warp;
+    if (q >= p.Qpad) return;
+    if (q >= p.Q) {   // padding entries of the threshold arrays: never pass
+        if (lane == 0) {
+            p.thrT[q] = __int_as_float(0x7f800000);
+            p.thrK[q] = 0ull;
+        }
+        return;
+    }
+    uint64_t* keys = skeys + (size_t)warp * (p.k + p.cap);
+    uint32_t cnt = p.fixed_cnt >= 0 ? (uint32_t)p.fixed_cnt : p.cnt[q];
+    if (cnt > p.cap) {
+        if (lane == 0) atomicAdd(p.overflow, 1u);
+        cnt = p.cap;
+    }
+    const uint32_t nbest = p.first ? 0u : p.k;
+    const uint32_t n = nbest + cnt;
+    uint64_t my_min = kNone;
+    uint32_t my_pos = 0;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint64_t key = i < nbest ? p.best[(size_t)q * p.k + i] : p.cand[(size_t)q * p.cap + (i - nbest)];
+        keys[i] = key;
+        if (key < my_min) {
+            my_min = key;
+            my_pos = i;
+        }
+    }
+    __syncwarp();
+    uint64_t kth = kNone;
+    for (uint32_t t = 0; t < p.k; ++t) {
+        uint64_t m = my_min;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, m, o);
+            m = other < m ? other : m;
+        }
+        if (m != kNone && my_min == m) {   // keys are unique: exactly one owner
+            keys[my_pos] = kNone;
+            my_min = kNone;
+            for (uint32_t i = lane; i < n; i += 32) {
+                const uint64_t key = keys[i];
+                if (key < my_min) {
+                    my_min = key;
+                    my_pos = i;
+                }
+            }
+        }
+        if (lane == 0) {
+            const size_t o = (size_t)q * p.k + t;
+            p.best[o] = m;
+            if (p.out_keys) p.out_keys[o] = m;
+            if (p.out_rows) p.out_rows[o] = m == kNone ? kNone : (m & ((1ull << kGlobalRowBits) - 1ull));
+            if (p.out_dists) p.out_dists[o] = m == kNone ? kNone : (m >> kGlobalRowBits);
+        }
+        kth = m;
+    }
+    if (lane == 0) {
+        p.thrK[q] = kth;
+        p.thrT[q] = kth == kNone ? __int_as_float(0xff800000)
+                                 : (float)((int)p.bits - 2 * (int)(kth >> kGlobalRowBits));
+        if (p.fixed_cnt < 0) p.cnt[q] = 0;
+    }
+}
+
 cudaError_t launch_mma_select(const MmaSelectParams& p, cudaStream_t stream) {
+    if (p.k <= 32 && (size_t)(p.k + p.cap) * 8 * kSelectWarps <= 160 * 1024) {
+        const size_t smem = (size_t)(p.k + p.cap) * 8 * kSelectWarps;
+        cudaError_t e =
+            cudaFuncSetAttribute(mma_select_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        mma_select_warp_kernel<<<(p.Qpad + kSelectWarps - 1) / kSelectWarps, kSelectWarps * 32, smem, stream>>>(p);
+        count_launch();
+        return cudaGetLastError();
+    }
     const size_t smem = (size_t)p.sort_cap * 8;
     cudaError_t e = cudaFuncSetAttribute(mma_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
