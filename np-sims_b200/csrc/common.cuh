@@ -45,6 +45,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Same, for roles with slack: try_wait with a suspend-time hint, so that the warp sleeps in hardware
+// until the phase completes (or the hint expires) instead of polling through issue slots.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+    } while (!ok);
+}
 
 // ---- TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier --------------
 // (SASS: UBLKCP).  dst/src 16-byte aligned, bytes a non-zero multiple of 16.

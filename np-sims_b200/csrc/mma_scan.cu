@@ -390,21 +390,33 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
             for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
                 const unsigned long long row0 = (unsigned long long)phase_tile(p, i) * kMmaTileRows;
                 const bool valid = row0 + u < p.N;
-                mbar_wait(&p_full[ps], pph);
+                mbar_wait_relaxed(&p_full[ps], pph);
                 if (u == 0 && part == 0) NPS_TRACE(1, 3);   // packed tile landed
                 const uint64_t* my = reinterpret_cast<const uint64_t*>(smem + L.p_off + ps * L.p_stride) + (size_t)u * W;
                 const uint32_t mw = t_idx & 1u;
                 uint32_t lg = mw ? lg2[1] : lg2[0];
                 for (uint32_t g = 0; g < GPT; ++g, ++lg) {
                     const uint32_t slot = mw * RG + (lg & (RG - 1u)), par = (lg >> (RG - 1u)) & 1u;
-                    mbar_wait(&g_empty[slot], par ^ 1u);
+                    mbar_wait_relaxed(&g_empty[slot], par ^ 1u);
                     if (u == 0 && part == 0) NPS_TRACE(1, 1);   // group free
                     const uint32_t kb0 = g * GS, kb1 = min(kb0 + GS, KB);
                     for (uint32_t kb = kb0; kb < kb1; ++kb) {
+                        // this thread's two words of the K-block (4 kb + 2 part, + 1): ONE 16-byte load when
+                        // the row width is even (row strides of 64/128/256 bytes put every lane of a warp on
+                        // the same banks; four 8-byte loads per thread cost ~1000 cycles per K-block there)
                         const uint32_t nw = valid ? min(4u, W - 4u * kb) : 0u;
-                        uint64_t w[4];
-#pragma unroll
-                        for (uint32_t j = 0; j < 4; ++j) w[j] = j < nw ? my[4 * kb + j] : 0ull;
+                        uint64_t w[4] = {0ull, 0ull, 0ull, 0ull};
+                        const uint32_t j0 = 2u * part;
+                        if ((W & 1u) == 0u) {
+                            if (j0 < nw) {
+                                const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(my + 4 * kb + j0);
+                                w[j0] = t.x;
+                                w[j0 + 1] = t.y;
+                            }
+                        } else {
+                            if (j0 < nw) w[j0] = my[4 * kb + j0];
+                            if (j0 + 1 < nw) w[j0 + 1] = my[4 * kb + j0 + 1];
+                        }
                         if (!(p.debug & 2u))
                             expand(base + L.a_off + (slot * GS + (kb - kb0)) * kMmaAStageBytes, u, w, nw);
                     }
@@ -464,7 +476,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * NT + c0;
                 uint32_t staged = 0;   // survivors of this tile waiting in the staging buffer
                 NPS_DEV(const long long pc0 = prof_on ? clock64() : 0;)
-                mbar_wait(&acc_full[buf], (t_idx >> 1) & 1u);
+                mbar_wait_relaxed(&acc_full[buf], (t_idx >> 1) & 1u);
                 tc_fence_after();
                 NPS_DEV(const long long pc1 = prof_on ? clock64() : 0; prof_wait += pc1 - pc0;)
                 if (ew == 0 && lane == 0) NPS_TRACE(2, 1);   // accumulator ready
@@ -810,6 +822,8 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
     uint32_t growth = cap / (4u * k);
     if (growth > 8u) growth = 8u;
     if (growth < 2u) growth = 2u;
+    if (const char* e = getenv("NPS_MMA_CAP")) cap = (uint32_t)atoi(e);          // development
+    if (const char* e = getenv("NPS_MMA_GROWTH")) growth = (uint32_t)atoi(e);    // development
     pl->cap = cap;
     pl->growth = growth;
     pl->sort_cap = pow2_ceil(k + cap);
@@ -829,7 +843,9 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
     uint32_t np = 0;
     exps[np++] = e0;
     for (uint32_t e = e0; e > 0;) {
-        const uint32_t step = e <= 3 ? 1u : (e - 3 < gshift ? e - 3 : gshift);
+        uint32_t late = 3;   // number of final phases that only double
+        if (const char* ev = getenv("NPS_MMA_LATE")) late = (uint32_t)atoi(ev);   // development
+        const uint32_t step = e <= late ? 1u : (e - late < gshift ? e - late : gshift);
         e -= step;
         if (np == kMmaMaxPhases) return false;
         exps[np++] = e;
