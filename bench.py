@@ -48,6 +48,15 @@ WORKLOADS = {
 L2_FLUSH_BYTES = 256 << 20
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(path)).get(kernel)
+    except (OSError, ValueError):
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -344,7 +353,7 @@ def run_b200(args, wl):
         roofline = {
             "kernel": f"mma_scan_kernel<dense=false> (tcgen05 kind::mxf4, M128 x N{plan['n_tile']} x K64), phase {dom} of {nph}",
             "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
-            "traffic": None,
+            "traffic": ncu_traffic("mma_scan_kernel") if (world == 1 and wl is WORKLOADS["c2"]) else None,
             "peak_source": "4 x measured bf16 burst (MEASURED_PEAKS.json): mxf4 : bf16 = 9 : 2.25 PFLOP/s nominal; "
                            "scripts/ubench/umma_mxf4_probe measured 16359 MAC/clk/SM issue rate in-kernel",
             "ms_per_launch": ph_ms[dom], "share_of_step": ph_ms[dom] / step_ms,
@@ -369,8 +378,9 @@ def run_b200(args, wl):
         roofline = {
             "kernel": f"scan_topk_kernel<W={words},R={plan['rows_per_thread']}>",
             "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-            "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-            "ms_per_launch": scan_avg, "share_of_step": scan_avg / step_ms,
+            "frac": achieved_gbs / hbm_peak,
+            "traffic": ncu_traffic("scan_topk_kernel") if (world == 1 and wl is WORKLOADS["c2"]) else None,
+            "peak_source": peak_src, "ms_per_launch": scan_avg, "share_of_step": scan_avg / step_ms,
             "note": ("at this batch size the scan re-reads an L2-resident table once per query tile and is bound "
                      "by the integer POPC pipe, not HBM; see `popc` for that roofline and `roofline_stream` for "
                      "the HBM-bound single-query scan"),
