@@ -221,7 +221,7 @@ def run_b200(args, wl):
     import np_sims
     import np_sims.lsh as lsh
     from np_sims import _lib
-    from np_sims.sharded import ShardedIndex, shard_bounds
+    from np_sims.sharded import ReplicatedIndex, ShardedIndex, choose_sharding, query_bounds, shard_bounds
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,13 +233,20 @@ def run_b200(args, wl):
     dev = torch.device("cuda", local_rank)
     hbm_peak, peak_src, sm_max_mhz = peaks()
     k, nq, words = wl["k"], wl["queries"], wl["bits"] // 64
+    shard = args.shard if args.shard != "auto" else choose_sharding(wl["rows"], words, nq, world)
+    if world == 1:
+        shard = "rows"
+    by_query = shard == "queries"
+    qb = query_bounds(nq, world) if by_query else [0] * rank + [0, nq]
+    qlo, qhi = qb[rank], qb[rank + 1]        # the queries THIS rank hashes and answers
 
     # ---- inputs (synthetic), resident in HBM before timing
+    b = [0] * (rank + 1) + [wl["rows"]] if by_query else shard_bounds(wl["rows"], world)
     if wl["dims"]:
         W = make_projections(wl["bits"], wl["dims"])
-        qvecs_host = make_vectors(nq, wl["dims"], 1)
+        qvecs_all = make_vectors(nq, wl["dims"], 1)
+        qvecs_host = qvecs_all[qlo:qhi]
         X = make_vectors(wl["rows"], wl["dims"], 0)
-        b = shard_bounds(wl["rows"], world)
         t0 = time.perf_counter()
         H_local = lsh.hash_vectors(torch.from_numpy(X[b[rank]:b[rank + 1]]).to(dev), W)   # K1: index build
         torch.cuda.synchronize()
@@ -248,30 +255,36 @@ def run_b200(args, wl):
         qvecs_pinned = torch.from_numpy(qvecs_host).pin_memory()
     else:   # signature-only workload (C4): i.i.d. bits drawn on the device, one generator stream per shard
         W = None
-        b = shard_bounds(wl["rows"], world)
         g = torch.Generator(device=dev)
-        g.manual_seed(3 + rank)
+        g.manual_seed(3 + (0 if by_query else rank))
         H_local = torch.randint(-2**63, 2**63 - 1, (b[rank + 1] - b[rank], words), dtype=torch.int64, device=dev,
                                 generator=g)
         g.manual_seed(4)
-        qsig_dev = torch.randint(-2**63, 2**63 - 1, (nq, words), dtype=torch.int64, device=dev, generator=g)
+        qsig_dev = torch.randint(-2**63, 2**63 - 1, (nq, words), dtype=torch.int64, device=dev,
+                                 generator=g)[qlo:qhi].contiguous()
         qsig_pinned = qsig_dev.cpu().pin_memory()
         index_s = None
-    index = ShardedIndex(H_local, b[rank])
+    index = ReplicatedIndex(H_local) if by_query else ShardedIndex(H_local, b[rank])
     out_pinned = torch.empty((nq, k), dtype=torch.int64).pin_memory()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
+    def search(sigs):
+        """-> (rows, dists) [nq, k] for the WHOLE batch, on every rank."""
+        if by_query:      # ids only, like the reference's hamming_top_10: one all-gather
+            return index.gather(index.query_local(sigs, k, return_distances=False), nq), None
+        return index.query(sigs, k)
+
     def step_device():
         sigs = lsh.hash_vectors(qvecs_dev, W) if W is not None else qsig_dev
-        return index.query(sigs, k)
+        return search(sigs)
 
     def step_e2e():
         if W is not None:
             sigs = lsh.hash_vectors(qvecs_pinned.to(dev, non_blocking=True), W)
         else:
             sigs = qsig_pinned.to(dev, non_blocking=True)
-        rows, _ = index.query(sigs, k)
-        out_pinned.copy_(rows)            # D2H of the step's result (blocking)
+        rows, _ = search(sigs)
+        out_pinned.copy_(rows.view(torch.int64))            # D2H of the step's result (blocking)
         return out_pinned
 
     def timed(fn, steps, warmup):
@@ -331,6 +344,7 @@ def run_b200(args, wl):
     _lib.raw("nps_profile_enable")(0)
     scan_avg = float(np.mean(scan_ms))
     n_local = b[rank + 1] - b[rank]
+    nq_local = qhi - qlo
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max_mhz
     step_ms = total_ms / args.steps
     if phase_runs:
@@ -347,9 +361,9 @@ def run_b200(args, wl):
         ph_ms = [float(np.mean([r[j][1] for r in phase_runs])) for j in range(nph)]
         dom = int(np.argmax(ph_ms))
         rows_dom = min(tiles[dom] * 128, n_local)
-        flop_dom = 2.0 * rows_dom * nq * wl["bits"]
+        flop_dom = 2.0 * rows_dom * nq_local * wl["bits"]
         ach = flop_dom / (ph_ms[dom] * 1e-3) / 1e12
-        flop_all = 2.0 * n_local * nq * wl["bits"]
+        flop_all = 2.0 * n_local * nq_local * wl["bits"]
         roofline = {
             "kernel": f"mma_scan_kernel<dense=false> (tcgen05 kind::mxf4, M128 x N{plan['n_tile']} x K64), phase {dom} of {nph}",
             "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
@@ -357,13 +371,13 @@ def run_b200(args, wl):
             "peak_source": "4 x measured bf16 burst (MEASURED_PEAKS.json): mxf4 : bf16 = 9 : 2.25 PFLOP/s nominal; "
                            "scripts/ubench/umma_mxf4_probe measured 16359 MAC/clk/SM issue rate in-kernel",
             "ms_per_launch": ph_ms[dom], "share_of_step": ph_ms[dom] / step_ms,
-            "algorithmic": {"rows": rows_dom, "queries": nq, "bits": wl["bits"], "flop": flop_dom},
+            "algorithmic": {"rows": rows_dom, "queries": nq_local, "bits": wl["bits"], "flop": flop_dom},
             "phases": [{"tiles": t, "scan_ms": m} for t, m in zip(tiles, ph_ms)],
             "all_phases": {"scan_ms": float(np.sum(ph_ms)), "scan_plus_select_ms": scan_avg,
                            "achieved_tflops": flop_all / (scan_avg * 1e-3) / 1e12,
                            "frac": flop_all / (scan_avg * 1e-3) / 1e12 / tensor_peak},
             "plan": plan,
-            "popc_equivalent": {"gpopc32_s": 2.0 * n_local * nq * words / (scan_avg * 1e-3) / 1e9,
+            "popc_equivalent": {"gpopc32_s": 2.0 * n_local * nq_local * words / (scan_avg * 1e-3) / 1e9,
                                 "popc_pipe_peak_gpopc32_s": 148 * 16 * sm_mhz * 1e6 / 1e9,
                                 "note": "the XOR+POPC formulation of the same batch would need this POPC rate; "
                                         "the integer pipe peaks at 148 SM x 16 /clk"},
@@ -371,9 +385,9 @@ def run_b200(args, wl):
     else:
         plan = _lib.last_scan_plan()
         # algorithmic bytes of one scan launch: signatures + queries + results
-        alg_bytes = n_local * words * 8 + nq * words * 8 + nq * plan["num_chunks"] * k * 8
+        alg_bytes = n_local * words * 8 + nq_local * words * 8 + nq_local * plan["num_chunks"] * k * 8
         achieved_gbs = alg_bytes / (scan_avg * 1e-3) / 1e9
-        popc32 = 2.0 * n_local * nq * words
+        popc32 = 2.0 * n_local * nq_local * words
         popc_peak = 148 * 16 * sm_mhz * 1e6
         roofline = {
             "kernel": f"scan_topk_kernel<W={words},R={plan['rows_per_thread']}>",
@@ -399,27 +413,31 @@ def run_b200(args, wl):
             Wn = np.asarray(W)
             H_host = H_local.cpu().numpy().view(np.uint64)
             # parity of the timed step against the oracle on a handful of queries
-            sig_host = oracle.index_np(qvecs_host[:4], Wn)
+            sig_host = oracle.index_np(qvecs_all[:4], Wn)
             got = rows[:4].cpu().numpy().view(np.uint64)
             for i in range(4):
                 want, _ = oracle.top_k_canonical(H_host, sig_host[i], k)
                 assert np.array_equal(got[i], want), "timed step disagrees with the oracle"
-            _, _, cpu = cpu_reference_run(wl, args.cpu_sample, steps=64, warmup=1, H=H_host, W=Wn, qvecs=qvecs_host,
+            _, _, cpu = cpu_reference_run(wl, args.cpu_sample, steps=64, warmup=1, H=H_host, W=Wn, qvecs=qvecs_all,
                                           time_budget_s=20.0)
-        h2d = (qvecs_host.nbytes if W is not None else nq * words * 8)
+        # summed over ranks: row sharding uploads the whole batch on every rank, query sharding one slice each
+        h2d = (qvecs_all.nbytes if W is not None else nq * words * 8) * (1 if by_query else world)
         line = {
             "metric": "hamming_top_n queries/s", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
             "config": {"workload": wl["desc"], "rows": wl["rows"], "bits": wl["bits"], "queries": nq, "k": k,
-                       "parallelism": f"row-sharded x{world}" + (" + NCCL all-gather of candidate keys" if world > 1 else ""),
-                       "step": "hash query batch (K1) + batched scan/top-n (K2T tensor-core phases + select)" + (" + all-gather + K4 merge" if world > 1 else ""),
+                       "parallelism": (f"table replicated, query batch sharded x{world} + NCCL all-gather of results"
+                                       if by_query else
+                                       f"row-sharded x{world}" + (" + NCCL all-gather of candidate keys" if world > 1 else "")),
+                       "step": "hash query batch (K1) + batched scan/top-n (K2T tensor-core phases + select)" +
+                               ((" + all-gather of results" if by_query else " + all-gather + K4 merge") if world > 1 else ""),
                        "l2": f"flushed between timed iterations ({L2_FLUSH_BYTES >> 20} MiB write)",
                        "index_build_s": index_s},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(nq * k * 8), "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": int(nq * k * 8) * world, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "roofline_stream": stream,
@@ -463,6 +481,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--shard", default="auto", choices=["auto", "rows", "queries"],
+                    help="N > 1: split the table by rows, or replicate it and split the query batch (auto: by table size)")
     ap.add_argument("--ref-sample", type=int, default=512, help="queries per step of the reference arm")
     ap.add_argument("--cpu-sample", type=int, default=256, help="queries per batch of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -193,6 +193,77 @@ static TopNWorkspace topn_workspace(const ScanPlan& pl, uint32_t Q, uint32_t k) 
     return w;
 }
 
+// The XOR+POPC scan (K2) + block merge (K3) over one batch of queries.  `gate` (device pointer or
+// null): when non-null every launch exits at once unless *gate != 0 — that is how the tensor-core
+// path repairs a candidate-buffer overflow on the device, with no host round trip.
+static int run_popc(const ScanPlan& pl, const uint64_t* d_hashes, uint64_t N, uint32_t W, const uint64_t* d_queries,
+                    uint32_t Q, uint32_t k, uint64_t row_base, uint64_t* d_rows, uint64_t* d_dists,
+                    uint64_t* d_keys_out, void* ws, const uint32_t* gate, bool profile, cudaStream_t stream) {
+    const TopNWorkspace w = topn_workspace(pl, Q, k);
+    uint64_t* keys = reinterpret_cast<uint64_t*>(ws);
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ws) + w.keys_bytes);
+
+    ScanParams p;
+    p.hashes = d_hashes;
+    p.queries = d_queries;
+    p.out_keys = keys;
+    p.gate = gate;
+    p.N = N;
+    p.row_base = row_base;
+    p.Q = Q;
+    p.k = k;
+    p.cap = pl.cap;
+    p.words = W;
+    p.chunk_rows = pl.chunk_rows;
+    p.num_chunks = pl.num_chunks;
+    p.q_tile = pl.q_tile;
+    p.num_qtiles = pl.num_qtiles;
+    p.row_bits = pl.row_bits;
+    p.stages = pl.stages;
+    p.tile_rows = pl.tile_rows;
+    if (profile) NPS_CUDA(cudaEventRecord(g_ev[0], stream));
+    if (pl.specialised) {
+        ScanLaunchFn fn = scan_launcher_for_width((int)W);
+        if (!fn) return fail(NPS_EINVAL, "no scan kernel for words=%u", W);
+        NPS_CUDA(fn(p, pl.grid, pl.smem, stream));
+    } else {
+        NPS_CUDA(launch_scan_generic(p, pl.grid, pl.smem, stream));
+    }
+    if (profile) NPS_CUDA(cudaEventRecord(g_ev[1], stream));
+    NPS_CUDA(launch_merge(keys, Q, pl.num_chunks, k, /*list_major=*/0, scratch, d_rows, d_dists, d_keys_out, stream,
+                          gate));
+    if (profile) NPS_CUDA(cudaEventRecord(g_ev[2], stream));
+    return NPS_OK;
+}
+
+// Device-side overflow repair of the tensor-core path: the same batch on K2/K3, in query slices
+// whose workspace stays under kRepairSliceBytes, every launch gated on the overflow counter.
+constexpr size_t kRepairSliceBytes = 256ull << 20;
+struct RepairPlan {
+    uint32_t slice_q;     // queries per slice
+    ScanPlan full, tail;  // plans of a full slice and of the last (shorter) one
+    size_t ws_bytes;
+};
+static int plan_repair(uint64_t N, uint32_t W, uint32_t Q, uint32_t k, const DeviceInfo& dev, RepairPlan* rp) {
+    uint32_t sq = Q;
+    for (;;) {
+        int rc = plan_scan(N, W, sq, k, dev.sm_count, dev.smem_optin, &rp->full);
+        if (rc) return rc;
+        if (topn_workspace(rp->full, sq, k).total <= kRepairSliceBytes || sq <= 64) break;
+        sq = (sq + 1) / 2;
+    }
+    rp->slice_q = sq;
+    rp->ws_bytes = topn_workspace(rp->full, sq, k).total;
+    rp->tail = rp->full;
+    if (Q % sq) {
+        int rc = plan_scan(N, W, Q % sq, k, dev.sm_count, dev.smem_optin, &rp->tail);
+        if (rc) return rc;
+        const size_t t = topn_workspace(rp->tail, Q % sq, k).total;
+        if (t > rp->ws_bytes) rp->ws_bytes = t;
+    }
+    return NPS_OK;
+}
+
 static int run_top_n(const uint64_t* d_hashes, uint64_t N, uint32_t W, const uint64_t* d_queries, uint32_t Q,
                      uint32_t k, uint64_t row_base, uint64_t* d_rows, uint64_t* d_dists, uint64_t* d_keys_out,
                      void* ws, size_t ws_bytes, cudaStream_t stream) {
@@ -210,7 +281,11 @@ static int run_top_n(const uint64_t* d_hashes, uint64_t N, uint32_t W, const uin
     if (Q == 0) return fail(NPS_EINVAL, "num_queries must be > 0");
     MmaPlan mp;
     if (choose_mma(N, W, Q, k, dev, &mp)) {
-        if (ws_bytes < mp.total || !ws) return fail(NPS_EWORKSPACE, "workspace %zu bytes < required %zu", ws_bytes, mp.total);
+        RepairPlan rp;
+        rc = plan_repair(N, W, Q, k, dev, &rp);
+        if (rc) return rc;
+        const size_t need = align256(mp.total) + rp.ws_bytes;
+        if (ws_bytes < need || !ws) return fail(NPS_EWORKSPACE, "workspace %zu bytes < required %zu", ws_bytes, need);
         if (reinterpret_cast<uintptr_t>(ws) & 255u) return fail(NPS_EINVAL, "workspace must be 256-byte aligned");
         g_last_path = NPS_SCAN_MMA;
         g_last_mma_plan = mp;
@@ -221,10 +296,19 @@ static int run_top_n(const uint64_t* d_hashes, uint64_t N, uint32_t W, const uin
         }
         NPS_CUDA(run_mma_top_n(mp, d_hashes, N, W, d_queries, Q, k, row_base, d_rows, d_dists, d_keys_out, ws, stream,
                                g_profile ? g_phase_ev : nullptr));
-        if (g_profile) {
-            NPS_CUDA(cudaEventRecord(g_ev[1], stream));   // scan = all phases (scan + select launches)
-            NPS_CUDA(cudaEventRecord(g_ev[2], stream));
+        if (g_profile) NPS_CUDA(cudaEventRecord(g_ev[1], stream));   // scan = all phases (scan + select launches)
+        // repair: the overflow counter is the first word of the workspace (mma_scan.cu)
+        const uint32_t* gate = reinterpret_cast<const uint32_t*>(ws);
+        void* rws = reinterpret_cast<uint8_t*>(ws) + align256(mp.total);
+        for (uint32_t q0 = 0; q0 < Q; q0 += rp.slice_q) {
+            const uint32_t nq = Q - q0 < rp.slice_q ? Q - q0 : rp.slice_q;
+            const size_t o = (size_t)q0 * k;
+            rc = run_popc(nq == rp.slice_q ? rp.full : rp.tail, d_hashes, N, W, d_queries + (size_t)q0 * W, nq, k,
+                          row_base, d_rows ? d_rows + o : nullptr, d_dists ? d_dists + o : nullptr,
+                          d_keys_out ? d_keys_out + o : nullptr, rws, gate, false, stream);
+            if (rc) return rc;
         }
+        if (g_profile) NPS_CUDA(cudaEventRecord(g_ev[2], stream));   // "merge" slot = the gated repair launches
         return NPS_OK;
     }
     g_last_path = NPS_SCAN_POPC;
@@ -235,45 +319,15 @@ static int run_top_n(const uint64_t* d_hashes, uint64_t N, uint32_t W, const uin
     if (ws_bytes < w.total || (!ws && w.total))
         return fail(NPS_EWORKSPACE, "workspace %zu bytes < required %zu", ws_bytes, w.total);
     if (reinterpret_cast<uintptr_t>(ws) & 15u) return fail(NPS_EINVAL, "workspace must be 16-byte aligned");
-    uint64_t* keys = reinterpret_cast<uint64_t*>(ws);
-    uint64_t* scratch = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ws) + w.keys_bytes);
-
-    ScanParams p;
-    p.hashes = d_hashes;
-    p.queries = d_queries;
-    p.out_keys = keys;
-    p.N = N;
-    p.row_base = row_base;
-    p.Q = Q;
-    p.k = k;
-    p.cap = pl.cap;
-    p.words = W;
-    p.chunk_rows = pl.chunk_rows;
-    p.num_chunks = pl.num_chunks;
-    p.q_tile = pl.q_tile;
-    p.num_qtiles = pl.num_qtiles;
-    p.row_bits = pl.row_bits;
-    p.stages = pl.stages;
-    p.tile_rows = pl.tile_rows;
     g_last_plan = ScanPlanInfo{pl.tile_rows, pl.tile_bytes, pl.stages, pl.q_tile, pl.num_qtiles, pl.chunk_rows,
                                pl.num_chunks, pl.cap, pl.smem, (uint32_t)pl.grid, pl.specialised ? 1u : 0u,
                                pl.specialised ? (uint32_t)rows_per_thread((int)W) : 1u};
     if (g_profile) {
         rc = profile_events();
         if (rc) return rc;
-        NPS_CUDA(cudaEventRecord(g_ev[0], stream));
     }
-    if (pl.specialised) {
-        ScanLaunchFn fn = scan_launcher_for_width((int)W);
-        if (!fn) return fail(NPS_EINVAL, "no scan kernel for words=%u", W);
-        NPS_CUDA(fn(p, pl.grid, pl.smem, stream));
-    } else {
-        NPS_CUDA(launch_scan_generic(p, pl.grid, pl.smem, stream));
-    }
-    if (g_profile) NPS_CUDA(cudaEventRecord(g_ev[1], stream));
-    NPS_CUDA(launch_merge(keys, Q, pl.num_chunks, k, /*list_major=*/0, scratch, d_rows, d_dists, d_keys_out, stream));
-    if (g_profile) NPS_CUDA(cudaEventRecord(g_ev[2], stream));
-    return NPS_OK;
+    return run_popc(pl, d_hashes, N, W, d_queries, Q, k, row_base, d_rows, d_dists, d_keys_out, ws, nullptr, g_profile,
+                    stream);
 }
 
 }  // namespace nps
@@ -379,7 +433,11 @@ size_t nps_hamming_top_n_workspace_bytes(uint64_t num_hashes, uint32_t words, ui
         return 0;
     }
     MmaPlan mp;
-    if (choose_mma(num_hashes, words, num_queries, k, dev, &mp)) return mp.total;
+    if (choose_mma(num_hashes, words, num_queries, k, dev, &mp)) {
+        RepairPlan rp;
+        if (plan_repair(num_hashes, words, num_queries, k, dev, &rp) != NPS_OK) return 0;
+        return align256(mp.total) + rp.ws_bytes;
+    }
     ScanPlan pl;
     if (plan_scan(num_hashes, words, num_queries, k, dev.sm_count, dev.smem_optin, &pl) != NPS_OK) return 0;
     return topn_workspace(pl, num_queries, k).total;

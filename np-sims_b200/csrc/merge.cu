@@ -28,7 +28,9 @@ __global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __rest
                                                           size_t q_stride, size_t list_stride,
                                                           uint32_t k, uint32_t G, uint64_t* __restrict__ out_keys,
                                                           uint64_t* __restrict__ out_rows,
-                                                          uint64_t* __restrict__ out_dists) {
+                                                          uint64_t* __restrict__ out_dists,
+                                                          const uint32_t* __restrict__ gate) {
+    if (gate != nullptr && *gate == 0u) return;   // gated repair launch (api.cu), nothing to repair
     extern __shared__ __align__(16) uint64_t skeys[];
     const uint32_t q = blockIdx.y, grp = blockIdx.x, lists_out = gridDim.x;
     const uint32_t g0 = grp * G;
@@ -74,7 +76,7 @@ size_t merge_scratch_keys(uint32_t Q, uint32_t lists, uint32_t k) {
 
 cudaError_t launch_merge(const uint64_t* keys, uint32_t Q, uint32_t lists, uint32_t k, int list_major,
                          uint64_t* scratch, uint64_t* out_rows, uint64_t* out_dists, uint64_t* out_keys,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const uint32_t* gate) {
     if (Q == 0 || k == 0) return cudaSuccess;
     const uint32_t G = merge_group_size(k);
     const size_t smem = (size_t)(G < lists ? G : lists) * k * sizeof(uint64_t);
@@ -92,7 +94,7 @@ cudaError_t launch_merge(const uint64_t* keys, uint32_t Q, uint32_t lists, uint3
         const uint32_t nxt = (cur_lists + G - 1) / G;
         uint64_t* dst = flip ? bufB : bufA;
         merge_lists_kernel<<<dim3(nxt, Q), 256, (size_t)G * k * 8, stream>>>(cur, cur_lists, q_stride, list_stride, k,
-                                                                             G, dst, nullptr, nullptr);
+                                                                             G, dst, nullptr, nullptr, gate);
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -104,7 +106,8 @@ cudaError_t launch_merge(const uint64_t* keys, uint32_t Q, uint32_t lists, uint3
     }
     // last pass: decoded ids/distances, or (out_keys) the merged key list itself
     merge_lists_kernel<<<dim3(1, Q), 256, smem, stream>>>(cur, cur_lists, q_stride, list_stride, k, G, out_keys,
-                                                          out_keys ? nullptr : out_rows, out_keys ? nullptr : out_dists);
+                                                          out_keys ? nullptr : out_rows, out_keys ? nullptr : out_dists,
+                                                          gate);
     count_launch();
     return cudaGetLastError();
 }

@@ -11,5 +11,5 @@ size_t merge_scratch_keys(uint32_t Q, uint32_t lists, uint32_t k);
 //   -> out_keys [Q, k] if out_keys != nullptr, else decoded rows/dists [Q, k]
 cudaError_t launch_merge(const uint64_t* keys, uint32_t Q, uint32_t lists, uint32_t k, int list_major,
                          uint64_t* scratch, uint64_t* out_rows, uint64_t* out_dists, uint64_t* out_keys,
-                         cudaStream_t stream);
+                         cudaStream_t stream, const uint32_t* gate = nullptr);
 }  // namespace nps

@@ -27,6 +27,7 @@ struct ScanParams {
     const uint64_t* hashes;    // [N, W]
     const uint64_t* queries;   // [Q, W]
     uint64_t* out_keys;        // [Q, num_chunks, k]
+    const uint32_t* gate;      // non-null: the launch is a no-op unless *gate != 0 (overflow repair)
     unsigned long long N;
     unsigned long long row_base;  // added to every emitted row id (shard offset)
     uint32_t Q, k, cap, words;
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     constexpr int G = EVEN ? gcd_int(V, 8) : 1;    // bank-conflict rotation period
     const uint32_t QSTRIDE = scan_q_stride(W);
 
+    if (p.gate != nullptr && *p.gate == 0u) return;   // gated repair launch, nothing to repair
     extern __shared__ __align__(128) uint8_t smem[];
     const ScanSmem L = scan_smem_layout(TILE_BYTES, p.stages, W, p.q_tile, p.cap);
     uint8_t* stage_base = smem + L.stage_off;
@@ -348,6 +350,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
 // memory, one row per thread, runtime word loop.  Same selection machinery.
 // =============================================================================================
 __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_generic_kernel(const ScanParams p) {
+    if (p.gate != nullptr && *p.gate == 0u) return;   // gated repair launch, nothing to repair
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t W = p.words, ROW_BYTES = W * 8, TILE_ROWS = p.tile_rows;
     const uint32_t TILE_BYTES = TILE_ROWS * ROW_BYTES;

@@ -100,9 +100,7 @@ def hamming_top_n(hashes, query, n=10, return_distances=False, order="canonical"
             ws = t.empty(ws_bytes, dtype=t.uint8, device=H.device)
             _lib.call("nps_hamming_top_n", ptr(H), m, w, ptr(Q), q, n, int(row_base), ptr(rows), ptr(dists),
                       ptr(ws), ws_bytes, stream_ptr())
-            _repair_overflow(lambda ws2, nb: _lib.call(
-                "nps_hamming_top_n", ptr(H), m, w, ptr(Q), q, n, int(row_base), ptr(rows), ptr(dists), ptr(ws2), nb,
-                stream_ptr()), ws, m, w, q, n, H.device)
+            _remember_workspace(ws)
         else:
             if row_base:
                 raise ValueError("row_base is only supported with order='canonical'")
@@ -120,22 +118,22 @@ def hamming_top_n(hashes, query, n=10, return_distances=False, order="canonical"
     return _finish(rows, single, host)
 
 
-def _repair_overflow(rerun, ws, m, w, q, n, device):
-    """Tensor-core scan only: its per-query candidate buffers are sized for ~4x the expected
-    number of survivors; if one overflowed (adversarial row order), redo the call on the
-    XOR+POPC scan, which has no such limit.  Costs one 4-byte D2H read per batched call."""
-    t = require_cuda()
-    if _lib.raw("nps_last_scan_path")() != _lib.SCAN_MMA:
-        return
-    if _lib.overflow_count(ptr(ws), stream_ptr()) == 0:
-        return
-    prev = _lib.set_scan_path(_lib.SCAN_POPC)
-    try:
-        nb = _lib.raw("nps_hamming_top_n_workspace_bytes")(m, w, q, n)
-        ws2 = t.empty(nb, dtype=t.uint8, device=device)
-        rerun(ws2, nb)
-    finally:
-        _lib.set_scan_path(prev)
+_last_ws = None
+
+
+def _remember_workspace(ws):
+    """Keep the last top-n workspace alive so `last_overflow_count` can read its overflow counter."""
+    global _last_ws
+    _last_ws = ws
+
+
+def last_overflow_count() -> int:
+    """Diagnostics: how many candidate-buffer overflows the last tensor-core top-n call saw.  A
+    non-zero count means the library repaired the call ON THE DEVICE by re-running it on the
+    XOR+POPC scan (gated launches in api.cu: run_top_n) — results are exact either way.  Syncs."""
+    if _last_ws is None or _lib.raw("nps_last_scan_path")() != _lib.SCAN_MMA:
+        return 0
+    return _lib.overflow_count(ptr(_last_ws), stream_ptr())
 
 
 def hamming_top_10(hashes, query):

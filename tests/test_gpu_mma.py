@@ -104,10 +104,10 @@ def test_mma_duplicates_and_index_ties(nps, force_mma):
     assert rows[5].tolist() == list(range(10))
 
 
-def test_mma_sorted_rows_overflow_falls_back_exactly(nps, force_mma):
-    # Rows sorted so that every later row is CLOSER to the queries than all earlier ones: the
-    # thresholds learnt from early phases never filter anything, the candidate buffers overflow and
-    # the Python layer must redo the call on the XOR+POPC scan.  Results stay exact.
+def test_mma_sorted_rows_never_overflow(nps, force_mma):
+    # Rows sorted so that every later row is CLOSER to the queries than all earlier ones.  The
+    # strided phase schedule samples the whole table early, so thresholds are tight by the time
+    # the bulk is scanned and nothing overflows.
     n, w = 40000, 4
     rng = np.random.default_rng(3)
     base = rand_sigs(rng, 1, w)[0]
@@ -118,8 +118,46 @@ def test_mma_sorted_rows_overflow_falls_back_exactly(nps, force_mma):
         for b in order[: flips[i]]:
             h[i, b // 64] ^= np.uint64(1) << np.uint64(b % 64)
     q = np.tile(base, (64, 1))
+    from np_sims import ufuncs
     rows, dists = check_against_oracle(nps, h, q, 10, [0, 63])
     assert dists[0][0] == 0
+    assert ufuncs.last_overflow_count() == 0
+
+
+def test_mma_overflow_is_repaired_on_device(nps, force_mma):
+    # Adversarial for the phase schedule itself: odd 128-row tiles are visited only by the LAST
+    # phase, so put every near row there and only far rows in the even tiles.  Thresholds learnt
+    # from the even tiles filter nothing, far more than `cap` candidates per query arrive in one
+    # phase, the candidate buffers overflow, and the library must repair the call on the device
+    # (gated XOR+POPC launches, api.cu: run_top_n).  Results stay exact.
+    from np_sims import ufuncs
+    n, w, nq = 40_000, 4, 70
+    rng = np.random.default_rng(5)
+    base = rand_sigs(rng, 1, w)[0]
+    h = np.tile(base, (n, 1))
+    odd = ((np.arange(n) // 128) & 1) == 1
+    flips = np.where(odd, rng.integers(0, 100, size=n), rng.integers(150, 250, size=n))
+    order = rng.permutation(64 * w)
+    for i in range(n):
+        for b in order[: flips[i]]:
+            h[i, b // 64] ^= np.uint64(1) << np.uint64(b % 64)
+    q = np.tile(base, (nq, 1))
+    q[1:, 0] ^= rng.integers(0, 16, size=nq - 1).astype(np.uint64)
+    for k in (10, 100):
+        check_against_oracle(nps, h, q, k, [0, 1, nq - 1])
+        assert ufuncs.last_overflow_count() > 0, "the case is meant to overflow the candidate buffers"
+    # sharded keys entry point takes the same repair
+    import torch
+    from np_sims.sharded import _cuda_local_keys
+    keys = _cuda_local_keys(torch.from_numpy(h.view(np.int64)).cuda(), torch.from_numpy(q.view(np.int64)).cuda(), 10, 1000)
+    assert ufuncs.last_overflow_count() > 0
+    want_r, want_d = oracle.top_k_canonical(h, q[3], 10)
+    got = keys[3].cpu().numpy().view(np.uint64)
+    assert np.array_equal(got & np.uint64((1 << 40) - 1), want_r + np.uint64(1000))
+    assert np.array_equal(got >> np.uint64(40), want_d)
+    # a benign table right after: no overflow, the gated repair launches stay no-ops
+    check_against_oracle(nps, rand_sigs(rng, n, w), rand_sigs(rng, 64, w), 10, [0, 63])
+    assert ufuncs.last_overflow_count() == 0
 
 
 def test_mma_row_base_and_keys(nps, force_mma):

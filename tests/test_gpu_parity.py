@@ -383,3 +383,24 @@ def test_tensor_core_hash_degenerate_inputs(nps):
     W2 = lsh.create_projections(64, 63)
     assert np.array_equal(np.asarray(lsh.index(X2, W2)), oracle.index_np(X2, np.asarray(W2)))
     assert lsh.last_hash_stats["path"] == "f64"
+
+
+@pytest.mark.gpu
+def test_replicated_index_query_slices_equal_single_shot(nps):
+    # query-sharded mode (table replicated): answering the batch slice by slice == one call
+    import torch
+    from np_sims.sharded import ReplicatedIndex, query_bounds
+    rng = np.random.default_rng(78)
+    n, w, nq, k, G = 20_011, 10, 301, 10, 3
+    h = rand_sigs(rng, n, w, live_bits=40)
+    q = rand_sigs(rng, nq, w, live_bits=40)
+    want_r, want_d = nps.hamming_top_n(h, q, k, return_distances=True)
+    ix = ReplicatedIndex(torch.from_numpy(h.view(np.int64)).cuda())
+    Q = torch.from_numpy(q.view(np.int64)).cuda()
+    b = query_bounds(nq, G)
+    parts = [ix.query_local(Q[b[g]:b[g + 1]], k) for g in range(G)]
+    rows = torch.cat([p[0].view(torch.int64) for p in parts]).cpu().numpy().view(np.uint64)
+    dists = torch.cat([p[1].view(torch.int64) for p in parts]).cpu().numpy().view(np.uint64)
+    assert np.array_equal(rows, want_r) and np.array_equal(dists, want_d)
+    full_r, full_d = ix.query(Q, k)          # world size 1: gather is the identity
+    assert np.array_equal(full_r.cpu().numpy().view(np.uint64), want_r)

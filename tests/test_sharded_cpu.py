@@ -89,3 +89,63 @@ def test_shard_bounds_cover_and_align():
             assert b[0] == 0 and b[-1] == n and len(b) == g + 1
             assert all(b[i] <= b[i + 1] for i in range(g))
             assert all(x % 2 == 0 for x in b[:-1])
+
+
+def _oracle_top_n(H, Q, k):
+    rows = np.empty((len(Q), k), dtype=np.uint64)
+    dists = np.empty((len(Q), k), dtype=np.uint64)
+    for i, q in enumerate(Q):
+        rows[i], dists[i] = oracle.top_k_canonical(H, q, k)
+    return torch.from_numpy(rows.view(np.int64)), torch.from_numpy(dists.view(np.int64))
+
+
+def _replicated_worker(rank, world, port, n, w, k, nq, out_dir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "np-sims_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from np_sims.sharded import ReplicatedIndex, query_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(321)
+    H = rng.integers(0, 2**64, size=(n, w), dtype=np.uint64) & np.uint64(0xFFFF)
+    Q = rng.integers(0, 2**64, size=(nq, w), dtype=np.uint64) & np.uint64(0xFFFF)
+    ix = ReplicatedIndex(H, top_n_fn=_oracle_top_n)
+    b = query_bounds(nq, world)
+    assert ix.my_slice(nq) == (b[rank], b[rank + 1])
+    rows, dists = ix.query(Q, k)
+    assert rows.shape == (nq, k)
+    np.save(os.path.join(out_dir, f"rows_{rank}.npy"), rows.numpy().view(np.uint64))
+    np.save(os.path.join(out_dir, f"dists_{rank}.npy"), dists.numpy().view(np.uint64))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,w,k,nq", [(501, 3, 10, 7), (40, 2, 100, 6)])
+def test_two_rank_query_sharded_equals_single_shot(tmp_path, n, w, k, nq):
+    """Replicated table, ragged query slices (7 = 3 + 4): every rank ends with the full result."""
+    world = 2
+    mp.spawn(_replicated_worker, args=(world, _free_port(), n, w, k, nq, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(321)
+    H = rng.integers(0, 2**64, size=(n, w), dtype=np.uint64) & np.uint64(0xFFFF)
+    Q = rng.integers(0, 2**64, size=(nq, w), dtype=np.uint64) & np.uint64(0xFFFF)
+    r0, r1 = np.load(tmp_path / "rows_0.npy"), np.load(tmp_path / "rows_1.npy")
+    d0, d1 = np.load(tmp_path / "dists_0.npy"), np.load(tmp_path / "dists_1.npy")
+    assert np.array_equal(r0, r1) and np.array_equal(d0, d1)
+    for i in range(nq):
+        want_r, want_d = oracle.top_k_canonical(H, Q[i], k)
+        assert np.array_equal(r0[i], want_r) and np.array_equal(d0[i], want_d)
+
+
+def test_choose_sharding_and_query_bounds():
+    from np_sims.sharded import choose_sharding, query_bounds
+    assert choose_sharding(400_000, 10, 10_000, 1) == "rows"
+    assert choose_sharding(400_000, 10, 10_000, 8) == "queries"        # C2: 32 MB table
+    assert choose_sharding(100_000_000, 16, 100_000, 8) == "rows"      # C4: 12.8 GB table
+    assert choose_sharding(400_000, 10, 100, 8) == "rows"              # too few queries per rank
+    for q in (0, 1, 7, 10_000):
+        for g in (1, 2, 3, 8):
+            b = query_bounds(q, g)
+            assert b[0] == 0 and b[-1] == q and all(b[i] <= b[i + 1] for i in range(g))
