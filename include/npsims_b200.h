@@ -76,9 +76,10 @@ int nps_last_mma_plan(nps_mma_plan_t *out);
  * launch and the number of 128-row tiles it covered (phase 0 = dense bootstrap). */
 int nps_profile_last_phases(float *scan_ms, uint32_t *tiles, uint32_t max_phases, uint32_t *num_phases);
 /* Tensor-core path only: number of queries whose candidate buffer overflowed during the call
- * that used d_workspace (0 in all but adversarial inputs).  Synchronises the stream.  A caller
- * that sees a non-zero count repeats the call with NPS_SCAN_POPC (the host-level entry points
- * and the Python layer do this themselves). */
+ * that used d_workspace (0 in all but adversarial inputs).  Synchronises the stream.  Purely a
+ * diagnostic: when the count is non-zero the call has already been repaired ON THE DEVICE — every
+ * tensor-core top-n call enqueues the XOR+POPC scan + merge behind the phases, each launch gated
+ * on this counter, so results are exact either way and no caller action is needed. */
 int nps_top_n_overflow_count(const void *d_workspace, void *stream, uint32_t *out_count);
 /* cumulative number of CUDA kernels this library has launched in this process */
 unsigned long long nps_launch_count(void);
