@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __rest
                                                           const uint32_t* __restrict__ gate) {
     if (gate != nullptr && *gate == 0u) return;   // gated repair launch (api.cu), nothing to repair
     extern __shared__ __align__(16) uint64_t skeys[];
-    const uint32_t q = blockIdx.y, grp = blockIdx.x, lists_out = gridDim.x;
+    const uint32_t q = blockIdx.x, grp = blockIdx.y, lists_out = gridDim.y;   // queries on x: up to 2^31-1
     const uint32_t g0 = grp * G;
     const uint32_t g = (lists_in - g0) < G ? (lists_in - g0) : G;
     const uint32_t n = g * k;
@@ -93,7 +93,7 @@ cudaError_t launch_merge(const uint64_t* keys, uint32_t Q, uint32_t lists, uint3
     while (cur_lists > G) {
         const uint32_t nxt = (cur_lists + G - 1) / G;
         uint64_t* dst = flip ? bufB : bufA;
-        merge_lists_kernel<<<dim3(nxt, Q), 256, (size_t)G * k * 8, stream>>>(cur, cur_lists, q_stride, list_stride, k,
+        merge_lists_kernel<<<dim3(Q, nxt), 256, (size_t)G * k * 8, stream>>>(cur, cur_lists, q_stride, list_stride, k,
                                                                              G, dst, nullptr, nullptr, gate);
         count_launch();
         e = cudaGetLastError();
@@ -105,7 +105,7 @@ cudaError_t launch_merge(const uint64_t* keys, uint32_t Q, uint32_t lists, uint3
         flip ^= 1;
     }
     // last pass: decoded ids/distances, or (out_keys) the merged key list itself
-    merge_lists_kernel<<<dim3(1, Q), 256, smem, stream>>>(cur, cur_lists, q_stride, list_stride, k, G, out_keys,
+    merge_lists_kernel<<<dim3(Q, 1), 256, smem, stream>>>(cur, cur_lists, q_stride, list_stride, k, G, out_keys,
                                                           out_keys ? nullptr : out_rows, out_keys ? nullptr : out_dists,
                                                           gate);
     count_launch();

@@ -404,3 +404,17 @@ def test_replicated_index_query_slices_equal_single_shot(nps):
     assert np.array_equal(rows, want_r) and np.array_equal(dists, want_d)
     full_r, full_d = ix.query(Q, k)          # world size 1: gather is the identity
     assert np.array_equal(full_r.cpu().numpy().view(np.uint64), want_r)
+
+
+@pytest.mark.gpu
+def test_merge_more_than_65535_queries(nps):
+    # the C4 batch is 100k queries: the merge grid must not put queries on gridDim.y (max 65535)
+    import torch
+    from np_sims.sharded import _cuda_merge
+    rng = np.random.default_rng(79)
+    G, q, k = 3, 70_001, 4
+    keys = np.sort(rng.integers(0, 2**50, size=(G, q, k), dtype=np.uint64), axis=2)
+    rows, dists = _cuda_merge(torch.from_numpy(keys.view(np.int64)).cuda(), k)
+    want = np.sort(np.transpose(keys, (1, 0, 2)).reshape(q, -1), axis=1)[:, :k]
+    assert np.array_equal(rows.cpu().numpy().view(np.uint64), want & np.uint64((1 << 40) - 1))
+    assert np.array_equal(dists.cpu().numpy().view(np.uint64), want >> np.uint64(40))
