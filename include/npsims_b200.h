@@ -175,18 +175,23 @@ int nps_project_sign_pack_f64(const void *d_vectors, int vectors_are_f32, uint64
                               uint64_t *d_out, double *d_dots, void *stream);
 
 /* K1T — the same hashing for float32 vectors on the tensor cores: TMA-fed tcgen05 kind::tf32
- * GEMM with a sign/bit-pack epilogue.  Accumulators with |acc| < (2^-9 + dims * 2^-22) * |x_i| *
- * projection_norm_max cannot be trusted at TF32 precision; those (row, projection) pairs (a few
- * percent) are recomputed in float64 by a fix-up kernel, so the signatures equal those of
+ * GEMM with a sign/bit-pack epilogue.  Both operands are split into two TF32 terms (x = xh + xl in
+ * the kernel, w = wh + wl by nps_project_split_projections) and three products are accumulated, so
+ * an accumulator is exact to (5 + dims) * 2^-22 * |x_i| * projection_norm_max; the (row,
+ * projection) pairs below that (0.1 % at dims = 300) and all rows with a zero / tiny / huge /
+ * non-finite norm are recomputed in float64 by a fix-up kernel, so the signatures equal those of
  * nps_project_sign_pack_f64.  Needs dims % 4 == 0 and 16-byte aligned inputs.
- * d_projections_f32 / _f64: the same [num_projections, dims] matrix in both precisions;
+ * d_projections_split: float [2, num_projections, dims] from nps_project_split_projections (do it
+ * once per projection matrix); d_projections_f64: the float64 matrix (fix-up);
  * projection_norm_max = max_j |projections[j]| (1.0 for lsh.create_projections).
- * nps_project_sign_pack_stats (synchronises the stream) returns how many pairs were recomputed
- * and the fix-up list capacity; recomputed > capacity means entries were dropped and the caller
- * must redo the call with nps_project_sign_pack_f64 (the Python layer does). */
+ * If the fix-up list overflows (degenerate input) the call is redone in float64 by a gated launch
+ * on the device — no host round trip.  nps_project_sign_pack_stats (diagnostic; synchronises the
+ * stream) returns how many pairs went to the fix-up list and its capacity. */
+int nps_project_split_projections(const double *d_projections_f64, uint32_t num_projections, uint32_t dims,
+                                  float *d_out_split, void *stream);
 size_t nps_project_sign_pack_workspace_bytes(uint64_t num_vectors, uint32_t num_projections);
 int nps_project_sign_pack(const float *d_vectors, uint64_t num_vectors, uint32_t dims,
-                          const float *d_projections_f32, const double *d_projections_f64,
+                          const float *d_projections_split, const double *d_projections_f64,
                           uint32_t num_projections, float projection_norm_max, uint64_t *d_out,
                           void *d_workspace, size_t workspace_bytes, void *stream);
 int nps_project_sign_pack_stats(const void *d_workspace, uint64_t num_vectors, uint32_t num_projections,

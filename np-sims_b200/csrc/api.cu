@@ -536,6 +536,13 @@ size_t nps_project_sign_pack_workspace_bytes(uint64_t num_vectors, uint32_t num_
     return project_tc_workspace_bytes(num_vectors, num_projections, nullptr);
 }
 
+int nps_project_split_projections(const double* d_projections_f64, uint32_t num_projections, uint32_t dims,
+                                  float* d_out_split, void* stream) {
+    if (!d_projections_f64 || !d_out_split) return fail(NPS_EINVAL, "null pointer");
+    NPS_CUDA(launch_split_projections(d_projections_f64, num_projections, dims, d_out_split, (cudaStream_t)stream));
+    return NPS_OK;
+}
+
 int nps_project_sign_pack(const float* d_vectors, uint64_t num_vectors, uint32_t dims, const float* d_projections_f32,
                           const double* d_projections_f64, uint32_t num_projections, float projection_norm_max,
                           uint64_t* d_out, void* d_workspace, size_t workspace_bytes, void* stream) {

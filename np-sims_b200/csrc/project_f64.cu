@@ -18,18 +18,19 @@ namespace nps {
 
 constexpr int kPM = 64, kPN = 64, kPK = 16;
 
+// one 64-row x 64-projection tile (tile_x, tile_y)
 template <typename XT>
-__global__ void __launch_bounds__(256) project_f64_kernel(const XT* __restrict__ X, unsigned long long n_rows,
-                                                          uint32_t dims, const double* __restrict__ W,
-                                                          uint32_t n_proj, uint64_t* __restrict__ out,
-                                                          double* __restrict__ dots) {
+__device__ __forceinline__ void project_f64_tile(const XT* __restrict__ X, unsigned long long n_rows, uint32_t dims,
+                                                 const double* __restrict__ W, uint32_t n_proj,
+                                                 uint64_t* __restrict__ out, double* __restrict__ dots,
+                                                 unsigned long long tile_x, uint32_t tile_y) {
     __shared__ double xs[kPK][kPM + 1];
     __shared__ double ws[kPK][kPN + 1];
     __shared__ unsigned long long word_s[kPM];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;            // 16 x 16 threads, 4 x 4 outputs each
-    const unsigned long long row0 = (unsigned long long)blockIdx.x * kPM;
-    const uint32_t proj0 = blockIdx.y * kPN;
+    const unsigned long long row0 = tile_x * kPM;
+    const uint32_t proj0 = tile_y * kPN;
     double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -79,14 +80,47 @@ __global__ void __launch_bounds__(256) project_f64_kernel(const XT* __restrict__
     }
     __syncthreads();
     if (tid < kPM && row0 + tid < n_rows && out)
-        out[(row0 + tid) * (n_proj / 64) + blockIdx.y] = word_s[tid];
+        out[(row0 + tid) * (n_proj / 64) + tile_y] = word_s[tid];
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(256) project_f64_kernel(const XT* __restrict__ X, unsigned long long n_rows,
+                                                          uint32_t dims, const double* __restrict__ W,
+                                                          uint32_t n_proj, uint64_t* __restrict__ out,
+                                                          double* __restrict__ dots) {
+    project_f64_tile<XT>(X, n_rows, dims, W, n_proj, out, dots, blockIdx.x, blockIdx.y);
+}
+
+// Gated repair launch (project_tc.cu): a small persistent grid that does nothing unless the
+// tensor-core pass overflowed its fix-up list (*gate > gate_above), then redoes every tile.
+__global__ void __launch_bounds__(256) project_f64_gated_kernel(const float* __restrict__ X, unsigned long long n_rows,
+                                                                uint32_t dims, const double* __restrict__ W,
+                                                                uint32_t n_proj, uint64_t* __restrict__ out,
+                                                                const unsigned int* __restrict__ gate,
+                                                                unsigned int gate_above) {
+    if (*gate <= gate_above) return;
+    const unsigned long long tiles_x = (n_rows + kPM - 1) / kPM;
+    const uint32_t tiles_y = (n_proj + kPN - 1) / kPN;
+    for (unsigned long long t = blockIdx.x; t < tiles_x * tiles_y; t += gridDim.x) {
+        __syncthreads();
+        project_f64_tile<float>(X, n_rows, dims, W, n_proj, out, nullptr, t / tiles_y, (uint32_t)(t % tiles_y));
+    }
 }
 
 cudaError_t launch_project_f64(const void* X, int x_is_f32, unsigned long long n_rows, uint32_t dims,
-                               const double* W, uint32_t n_proj, uint64_t* out, double* dots, cudaStream_t stream) {
+                               const double* W, uint32_t n_proj, uint64_t* out, double* dots, cudaStream_t stream,
+                               const unsigned int* gate, unsigned int gate_above) {
     if (n_rows == 0) return cudaSuccess;
     const unsigned long long gx = (n_rows + kPM - 1) / kPM;
     if (gx > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+    if (gate) {
+        if (!x_is_f32 || dots) return cudaErrorInvalidValue;
+        const unsigned long long tiles = gx * ((n_proj + kPN - 1) / kPN);
+        project_f64_gated_kernel<<<(unsigned)(tiles < 2368 ? tiles : 2368), 256, 0, stream>>>(
+            (const float*)X, n_rows, dims, W, n_proj, out, gate, gate_above);
+        count_launch();
+        return cudaGetLastError();
+    }
     dim3 grid((unsigned)gx, (n_proj + kPN - 1) / kPN);
     if (x_is_f32)
         project_f64_kernel<float><<<grid, 256, 0, stream>>>((const float*)X, n_rows, dims, W, n_proj, out, dots);

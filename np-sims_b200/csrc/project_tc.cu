@@ -2,21 +2,35 @@
 // (replaces lsh.index / lsh.index_one, np_sims/lsh.py:31-44, for float32 vectors).
 //
 // The projection is a dense contraction, so it runs as a TMA-fed tcgen05 GEMM: 128-row tiles of X
-// and n_tile-projection tiles of W (both K-major fp32, SWIZZLE_128B boxes of 32 floats) stream
-// through a shared-memory ring; one elected thread issues tcgen05.mma kind::tf32 (M128 x N x K8)
-// into double-buffered TMEM accumulators; four epilogue warps read the accumulators back
-// (thread = row), turn 64 signs into one uint64 word of the signature (bit j of the row =
-// projection j >= 0, word j/64, bit j%64 — lsh.py:33) and store it.
+// and n_tile-projection tiles of W (K-major fp32, SWIZZLE_128B boxes of 32 floats) stream through
+// a shared-memory ring; one elected thread issues tcgen05.mma kind::tf32 (M128 x N x K8) into
+// double-buffered TMEM accumulators; four epilogue warps read the accumulators back (thread =
+// row), turn 64 signs into one uint64 word of the signature (bit j of the row = projection j >= 0,
+// word j/64, bit j%64 — lsh.py:33) and store it.
 //
-// Exactness.  The reference computes the dot products in float64; TF32 keeps 10 mantissa bits of
-// each operand, so an accumulator is only trusted when it is clearly away from zero:
-//      |acc| >= eps * |x_i| * max_j |w_j|,   eps = 2^-9 + dims * 2^-22
-// (truncation of both operands: <= 2^-10 relative each, summed against Cauchy-Schwarz; plus the
-// fp32 accumulation).  Every other (row, projection) pair — a few percent — goes to a fix-up list
-// and is recomputed in float64 by project_fix_kernel, which sets the bit the way the reference
-// would.  Signatures therefore agree with the float64 path bit for bit (up to float64 summation
-// order at |x.w| ~ 1e-16, as for project_f64.cu); the flipped-bit rate BEFORE fix-up is what the
-// tests report as the TF32 tolerance.
+// Exactness.  The reference computes the dot products in float64.  A single TF32 product keeps 11
+// significant bits per operand (relative error 2^-9 on the dot product: 2.8 % of all pairs at
+// D = 300 would be too close to zero to trust).  So both operands are split into two TF32 terms
+//      x = xh + xl (+ <= 2^-22 |x|)         w = wh + wl (+ <= 2^-22 |w|)
+// (xh = rn_tf32(x), xl = rn_tf32(x - xh): four splitter warps rewrite each X tile in shared memory
+// in place and emit the xl tile beside it; W is split once per projection matrix from its float64
+// values, nps_project_split_projections) and three products are accumulated:
+//      C1 += xh.wh            C2 += xh.wl + xl.wh          result = C1 + C2  (epilogue)
+// The small correction terms have their own accumulator so that their roundings are relative to
+// 2^-10 |x||w|, not |x||w|.  Error budget, relative to |x|_2 |w|_2 (Cauchy-Schwarz):
+//      representation  xl.wl + ex.w + x.ew                      <= 3.02 * 2^-22
+//      C1 accumulation D/8 instructions x 10 roundings x 2^-23   =  0.625 * D * 2^-22
+//                      (every addend aligned to the largest and truncated at 24 bits — the
+//                       zero-guard-bit model of the fp32 accumulate path; taken as D * 2^-22)
+//      C2 accumulation, final add                               <= (0.002 * D + 0.25) * 2^-22
+// An accumulator is trusted when |C1 + C2| >= eps |x_i| max_j |w_j|,  eps = (5 + D) * 2^-22
+// (7.3e-5 at D = 300: 0.1 % of all pairs; 1.8e-4 at D = 768: 0.4 %).  Every other (row,
+// projection) pair — and every row whose norm is not a comfortable float32 (zero, < 1e-18,
+// > 1e18, inf, NaN) — goes to a fix-up list and is recomputed in float64 by project_fix_kernel,
+// which sets the bit the way the reference would.  If the list overflows (degenerate input), a
+// gated launch of the float64 kernel redoes the whole call on the device.  Signatures therefore
+// agree with the float64 path bit for bit (up to float64 summation order at |x.w| ~ 1e-16, as for
+// project_f64.cu); the flipped-bit rate BEFORE fix-up is what the tests report as the tolerance.
 #include <cuda.h>
 
 #include <cstdio>
@@ -27,10 +41,10 @@
 
 namespace nps {
 
-constexpr int kPtThreads = 6 * 32;          // producer, MMA issuer, 4 epilogue warps
+constexpr int kPtThreads = 10 * 32;         // producer, MMA issuer, 4 epilogue warps, 4 splitter warps
 constexpr int kPtTileRows = 128;
 constexpr int kPtKBlock = 32;               // floats per K-block = one 128-byte swizzle row
-constexpr int kPtAStage = kPtTileRows * 128;
+constexpr int kPtAStage = kPtTileRows * 128;   // one X tile (xh or xl): 16 KB
 
 struct ProjTcParams {
     uint64_t* out;              // [N, B/64]
@@ -38,7 +52,7 @@ struct ProjTcParams {
     unsigned long long* fix;    // [fix_cap] row << 16 | projection
     unsigned int* fix_count;    // [1]
     unsigned long long N;
-    uint32_t D, B, n_tile, num_ntiles, stages, fix_cap;
+    uint32_t D, B, num_ntiles, stages, fix_cap;
     float tol_scale;            // eps * max_j |w_j|
     unsigned long long num_mtiles;
 };
@@ -57,6 +71,19 @@ __device__ __forceinline__ bool pt_elect_one() {
     return pred != 0;
 }
 
+__device__ __forceinline__ uint32_t rn_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+// x -> (xh, xl): both exactly representable in TF32, x - xh - xl <= 2^-22 |x|
+__device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& lo) {
+    hi = rn_tf32(__uint_as_float(x));
+    lo = rn_tf32(__uint_as_float(x) - __uint_as_float(hi));
+}
+
+// Stage layout: [xh tile 16 KB][xl tile 16 KB][wh tile NT x 128 B][wl tile NT x 128 B]
+template <uint32_t NT>
 __global__ void __launch_bounds__(kPtThreads, 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                   const ProjTcParams p) {
@@ -64,11 +91,13 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw);
-    const uint32_t NT = p.n_tile, S = p.stages;
-    const uint32_t stage_bytes = kPtAStage + NT * 128u;
+    const uint32_t S = p.stages;
+    constexpr uint32_t kWTile = NT * 128u;
+    constexpr uint32_t stage_bytes = 2u * kPtAStage + 2u * kWTile;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
-    uint64_t* full = bars;
-    uint64_t* empty = full + S;
+    uint64_t* full = bars;              // TMA landed (X raw + wh + wl)
+    uint64_t* split_done = full + S;    // splitter warps rewrote xh and wrote xl
+    uint64_t* empty = split_done + S;   // MMAs of the stage retired
     uint64_t* acc_full = empty + S;     // [2]
     uint64_t* acc_empty = acc_full + 2; // [2]
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc_empty + 2);
@@ -77,6 +106,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     if (tid == 0) {
         for (uint32_t s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
+            mbar_init(&split_done[s], 4);
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -95,7 +125,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const unsigned long long total = p.num_mtiles * p.num_ntiles;
 
     if (warp == 0) {
-        // ===== TMA producer: X tile (128 rows x 32 floats) + W tile (NT projections x 32 floats) per stage
+        // ===== TMA producer: X tile (128 rows x 32 floats) + the wh and wl tiles (NT projections x 32 floats)
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
             for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x) {
@@ -104,9 +134,10 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 for (uint32_t kb = 0; kb < KB; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1u);
                     const uint32_t dst = base + s * stage_bytes;
-                    mbar_arrive_expect_tx(&full[s], stage_bytes);
+                    mbar_arrive_expect_tx(&full[s], kPtAStage + 2u * kWTile);
                     tma_load_2d(dst, &tm_x, kb * kPtKBlock, (uint32_t)(mt * kPtTileRows), &full[s]);
-                    tma_load_2d(dst + kPtAStage, &tm_w, kb * kPtKBlock, nt * NT, &full[s]);
+                    tma_load_2d(dst + 2u * kPtAStage, &tm_w, kb * kPtKBlock, nt * NT, &full[s]);
+                    tma_load_2d(dst + 2u * kPtAStage + kWTile, &tm_w, kb * kPtKBlock, p.B + nt * NT, &full[s]);
                     if (++s == S) {
                         s = 0;
                         ph ^= 1u;
@@ -115,23 +146,29 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer
+        // ===== MMA issuer: C1 += xh.wh ; C2 += xh.wl + xl.wh
         const uint32_t idesc = umma_idesc(2, 2, kPtTileRows, NT);   // TF32 x TF32 -> F32
         uint32_t s = 0, ph = 0, t_idx = 0;
         for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx) {
             const uint32_t buf = t_idx & 1u;
             mbar_wait(&acc_empty[buf], ((t_idx >> 1) & 1u) ^ 1u);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + buf * NT;
+            const uint32_t c1 = tmem_base + buf * (2u * NT), c2 = c1 + NT;
             for (uint32_t kb = 0; kb < KB; ++kb) {
                 mbar_wait(&full[s], ph);
+                mbar_wait(&split_done[s], ph);
                 tc_fence_after();
                 if (pt_elect_one()) {
-                    const uint64_t a_desc = umma_desc_k_sw128(base + s * stage_bytes);
-                    const uint64_t b_desc = umma_desc_k_sw128(base + s * stage_bytes + kPtAStage);
+                    const uint32_t st = base + s * stage_bytes;
+                    const uint64_t xh = umma_desc_k_sw128(st), xl = umma_desc_k_sw128(st + kPtAStage);
+                    const uint64_t wh = umma_desc_k_sw128(st + 2u * kPtAStage);
+                    const uint64_t wl = umma_desc_k_sw128(st + 2u * kPtAStage + kWTile);
 #pragma unroll
-                    for (uint32_t j = 0; j < 4; ++j)    // K = 8 floats (32 bytes) per instruction
-                        umma_tf32(d_tmem, a_desc + 2u * j, b_desc + 2u * j, idesc, (kb | j) != 0u);
+                    for (uint32_t j = 0; j < 4; ++j) {   // K = 8 floats (32 bytes) per instruction
+                        umma_tf32(c1, xh + 2u * j, wh + 2u * j, idesc, (kb | j) != 0u);
+                        umma_tf32(c2, xh + 2u * j, wl + 2u * j, idesc, (kb | j) != 0u);
+                        umma_tf32(c2, xl + 2u * j, wh + 2u * j, idesc, true);
+                    }
                     umma_commit(&empty[s]);
                     if (kb + 1 == KB) umma_commit(&acc_full[buf]);
                 }
@@ -142,11 +179,42 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 }
             }
         }
+    } else if (warp >= 6) {
+        // ===== splitters: X tile (fp32 as TMA left it) -> xh in place + xl beside it.  Elementwise, so
+        // the 128-byte swizzle of the tile is irrelevant; 16-byte chunks, conflict-free.
+        const uint32_t sidx = (uint32_t)tid - 192u;
+        uint32_t s = 0, ph = 0;
+        for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x) {
+            for (uint32_t kb = 0; kb < KB; ++kb) {
+                mbar_wait(&full[s], ph);
+                uint4* xh = reinterpret_cast<uint4*>(smem + s * stage_bytes);
+                uint4* xl = xh + kPtAStage / 16;
+#pragma unroll
+                for (uint32_t i = 0; i < kPtAStage / 16 / 128; ++i) {
+                    const uint4 v = xh[sidx + i * 128u];
+                    uint4 h, l;
+                    split_tf32(v.x, h.x, l.x);
+                    split_tf32(v.y, h.y, l.y);
+                    split_tf32(v.z, h.z, l.z);
+                    split_tf32(v.w, h.w, l.w);
+                    xh[sidx + i * 128u] = h;
+                    xl[sidx + i * 128u] = l;
+                }
+                fence_proxy_async_smem();   // generic-proxy stores -> visible to tcgen05.mma (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&split_done[s]);
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
     } else {
-        // ===== epilogue: signs -> uint64 words, uncertain entries -> fix-up list
+        // ===== epilogue: signs -> uint64 words, uncertain entries -> fix-up list (one atomic per warp and item)
         const uint32_t quarter = warp & 3u;
         const uint32_t r_in_tile = quarter * 32u + lane;
         const uint32_t words_per_row = p.B / 64u;
+        constexpr uint32_t G = NT / 32u;       // 32-column groups per item
         uint32_t t_idx = 0;
         for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx) {
             const unsigned long long mt = item / p.num_ntiles;
@@ -154,56 +222,84 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const uint32_t buf = t_idx & 1u;
             const unsigned long long row = mt * kPtTileRows + r_in_tile;
             const bool valid = row < p.N;
-            const float tol = valid ? p.tol_scale * __ldg(p.norms + row) : 0.f;
+            const float norm = valid ? __ldg(p.norms + row) : 1.f;
+            const bool tame = norm >= 1e-18f && norm <= 1e18f;     // false for 0, tiny, huge, inf, NaN
+            const float tol = p.tol_scale * norm;
             mbar_wait(&acc_full[buf], (t_idx >> 1) & 1u);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * NT;
-            for (uint32_t c0 = 0; c0 < NT; c0 += 64u) {
-                uint32_t lohi[2];
+            const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * (2u * NT);
+            uint32_t sign_m[G], unsure_m[G];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t v[32];
-                    tmem_ld32(t_addr + c0 + h * 32u, v);
-                    tmem_ld_wait();
-                    uint32_t bits = 0, unsure = 0;      // per column: sign, |acc| below the tolerance
+            for (uint32_t g = 0; g < G; ++g) {
+                uint32_t v1[32], v2[32];
+                tmem_ld32(t_addr + g * 32u, v1);
+                tmem_ld32(t_addr + NT + g * 32u, v2);
+                tmem_ld_wait();
+                uint32_t bits = 0, unsure = 0;      // per column: sign, |acc| below the tolerance
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float a = __uint_as_float(v[j]);
-                        bits |= (a >= 0.f ? 1u : 0u) << j;
-                        unsure |= (fabsf(a) < tol ? 1u : 0u) << j;
-                    }
-                    lohi[h] = bits;
-                    // Fix-up list: ONE global atomic per warp and 32-column group (a per-entry atomic on
-                    // the single counter serialised in L2: measured 5 ms for 7 M entries).
-                    const uint32_t mine = __popc(unsure);
-                    uint32_t incl = mine;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += up;
-                    }
-                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                    if (total) {   // warp-uniform
-                        uint32_t basepos = 0;
-                        if (lane == 31) basepos = atomicAdd(p.fix_count, total);
-                        basepos = __shfl_sync(0xffffffffu, basepos, 31);
-                        uint32_t pos = basepos + incl - mine;
-                        const uint32_t col0 = nt * NT + c0 + h * 32u;
-                        for (uint32_t m = unsure; m; m &= m - 1u, ++pos)
-                            if (pos < p.fix_cap) p.fix[pos] = (row << 16) | (unsigned long long)(col0 + (__ffs(m) - 1));
-                    }
+                for (int j = 0; j < 32; ++j) {
+                    const float a = __uint_as_float(v1[j]) + __uint_as_float(v2[j]);
+                    bits |= (a >= 0.f ? 1u : 0u) << j;
+                    unsure |= (fabsf(a) < tol ? 1u : 0u) << j;
                 }
-                if (valid)
-                    p.out[row * words_per_row + (nt * NT + c0) / 64u] = (uint64_t)lohi[0] | ((uint64_t)lohi[1] << 32);
+                sign_m[g] = bits;
+                unsure_m[g] = !valid ? 0u : (tame ? unsure : 0xFFFFFFFFu);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);   // accumulator free before the global traffic below
+            if (valid) {
+#pragma unroll
+                for (uint32_t g = 0; g < G; g += 2)
+                    p.out[row * words_per_row + (nt * NT + g * 32u) / 64u] =
+                        (uint64_t)sign_m[g] | ((uint64_t)sign_m[g + 1] << 32);
+            }
+            uint32_t mine = 0;
+#pragma unroll
+            for (uint32_t g = 0; g < G; ++g) mine += __popc(unsure_m[g]);
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const uint32_t all = __shfl_sync(0xffffffffu, incl, 31);
+            if (all) {   // warp-uniform
+                uint32_t basepos = 0;
+                if (lane == 31) basepos = atomicAdd(p.fix_count, all);
+                basepos = __shfl_sync(0xffffffffu, basepos, 31);
+                uint32_t pos = basepos + incl - mine;
+#pragma unroll
+                for (uint32_t g = 0; g < G; ++g)
+                    for (uint32_t m = unsure_m[g]; m; m &= m - 1u, ++pos)
+                        if (pos < p.fix_cap)
+                            p.fix[pos] = (row << 16) | (unsigned long long)(nt * NT + g * 32u + (__ffs(m) - 1));
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// W (float64) -> [2, B, D] float32: wh = rn_tf32(w), wl = rn_tf32(w - wh); w - wh - wl <= 2^-22 |w|
+__global__ void __launch_bounds__(256) split_projections_kernel(const double* __restrict__ W, size_t n,
+                                                                float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const double w = W[i];
+    const uint32_t hi = rn_tf32((float)w);
+    const uint32_t lo = rn_tf32((float)(w - (double)__uint_as_float(hi)));
+    out[i] = __uint_as_float(hi);
+    out[n + i] = __uint_as_float(lo);
+}
+
+cudaError_t launch_split_projections(const double* W64, uint32_t B, uint32_t D, float* out, cudaStream_t stream) {
+    const size_t n = (size_t)B * D;
+    if (n == 0) return cudaSuccess;
+    split_projections_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(W64, n, out);
+    count_launch();
+    return cudaGetLastError();
 }
 
 // |x_i| for the tolerance test
@@ -289,7 +385,7 @@ size_t project_tc_workspace_bytes(unsigned long long N, uint32_t B, uint32_t* fi
     return ((size_t)N * 4 + 255) / 256 * 256 + 256 + (size_t)cap * 8;
 }
 
-cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, const float* W32, const double* W64,
+cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, const float* Wsplit, const double* W64,
                               uint32_t B, float w_norm_max, uint64_t* out, void* ws, int sm_count, int smem_optin,
                               cudaStream_t stream) {
     uint32_t fix_cap = 0;
@@ -308,37 +404,42 @@ cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, 
     p.N = N;
     p.D = D;
     p.B = B;
-    p.n_tile = (B % 256 == 0) ? 256 : (B % 128 == 0) ? 128 : 64;
-    p.num_ntiles = B / p.n_tile;
+    const uint32_t n_tile = (B % 128 == 0) ? 128 : 64;
+    p.num_ntiles = B / n_tile;
     p.num_mtiles = (N + kPtTileRows - 1) / kPtTileRows;
     p.fix_cap = fix_cap;
-    p.tol_scale = (1.0f / 512.0f + (float)D / 4194304.0f) * w_norm_max;
-    const uint32_t stage_bytes = kPtAStage + p.n_tile * 128u;
+    p.tol_scale = (5.0f + (float)D) / 4194304.0f * w_norm_max;      // eps = (5 + D) * 2^-22, see the header
+    const uint32_t stage_bytes = 2u * kPtAStage + 2u * n_tile * 128u;
     uint32_t stages = (uint32_t)((smem_optin - 2048) / (int)stage_bytes);
-    if (stages > 6) stages = 6;
+    if (stages > 4) stages = 4;
     if (stages < 2) return cudaErrorInvalidValue;
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
 
-    CUtensorMap tm_x, tm_w;
-    if (!make_tmap(&tm_x, X, N, D, kPtTileRows) || !make_tmap(&tm_w, W32, B, D, p.n_tile)) return cudaErrorInvalidValue;
+    CUtensorMap tm_x, tm_w;   // tm_w: the split projections [2B, D] (wh rows, then wl rows)
+    if (!make_tmap(&tm_x, X, N, D, kPtTileRows) || !make_tmap(&tm_w, Wsplit, 2ull * B, D, n_tile))
+        return cudaErrorInvalidValue;
 
     cudaError_t e = cudaMemsetAsync(fix_count, 0, 4, stream);
     if (e != cudaSuccess) return e;
     row_norm_kernel<<<(unsigned)((N + 7) / 8), 256, 0, stream>>>(X, N, D, norms);
     count_launch();
-    e = cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = n_tile == 128 ? project_tc_kernel<128> : project_tc_kernel<64>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned long long items = p.num_mtiles * p.num_ntiles;
     const int grid = (int)(items < (unsigned long long)sm_count ? items : (unsigned long long)sm_count);
-    project_tc_kernel<<<grid, kPtThreads, smem, stream>>>(tm_x, tm_w, p);
+    kern<<<grid, kPtThreads, smem, stream>>>(tm_x, tm_w, p);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     project_fix_kernel<<<sm_count * 8, 256, 0, stream>>>(fix, fix_count, fix_cap, X, W64, D, B,
                                                           reinterpret_cast<unsigned long long*>(out));
     count_launch();
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // fix-up list overflowed (degenerate input): redo the whole call in float64, on the device
+    return launch_project_f64(X, 1, N, D, W64, B, out, nullptr, stream, fix_count, fix_cap);
 }
 
 }  // namespace nps

@@ -55,6 +55,7 @@ _SIGS = {
     "nps_hamming_top_n_reference": (_int, [_vp, _u64, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _sz, _vp]),
     "nps_num_unshared_bits": (_int, [_vp, _u64, _vp, _u64, _u64, _vp, _vp]),
     "nps_project_sign_pack_workspace_bytes": (_sz, [_u64, _u32]),
+    "nps_project_split_projections": (_int, [_vp, _u32, _u32, _vp, _vp]),
     "nps_project_sign_pack": (_int, [_vp, _u64, _u32, _vp, _vp, _u32, ctypes.c_float, _vp, _vp, _sz, _vp]),
     "nps_project_sign_pack_stats": (_int, [_vp, _u64, _u32, _vp, ctypes.POINTER(_u32), ctypes.POINTER(_u32)]),
     "nps_project_sign_pack_f64": (_int, [_vp, _int, _u64, _u32, _vp, _u32, _vp, _vp, _vp]),

@@ -60,21 +60,39 @@ def _vectors_device(vectors):
     return t.from_numpy(arr).cuda()
 
 
-# Hashing statistics of the last tensor-core call: (row, projection) pairs whose TF32 accumulator
-# was too close to zero to trust and that were recomputed in float64 (tests / bench read this).
-last_hash_stats = {"path": None, "pairs": 0, "recomputed": 0}
+# Hashing statistics of the last call: path and number of (row, projection) pairs; `hash_stats()`
+# adds how many pairs the tensor-core pass sent to the float64 fix-up (synchronises).
+last_hash_stats = {"path": None, "pairs": 0, "recomputed": None}
+_last_hash_ws = None
 
 
-def _projections_f32(projections, P64):
-    """float32 copy of the projections and max_j |w_j| for the tensor-core pass (cached on the
-    DeviceArray next to the float64 upload)."""
+def hash_stats():
+    """Diagnostics (tests / bench): `last_hash_stats` with `recomputed` filled in — the number of
+    pairs whose accumulator was too close to zero to trust and that were recomputed in float64;
+    `overflowed` says the fix-up list was too small and the whole call was redone in float64 on
+    the device.  Synchronises the stream; the hashing call itself never does."""
+    st = dict(last_hash_stats)
+    if st["path"] == "tf32x3+fixup" and _last_hash_ws is not None:
+        import ctypes
+        ws, n, b = _last_hash_ws
+        fixed, cap = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        _lib.call("nps_project_sign_pack_stats", ptr(ws), n, b, stream_ptr(), ctypes.byref(fixed), ctypes.byref(cap))
+        st.update(recomputed=int(fixed.value), overflowed=fixed.value > cap.value)
+    return st
+
+
+def _projections_split(projections, P64):
+    """[2, B, D] float32 TF32 split of the projections (nps_project_split_projections) and
+    max_j |w_j| for the tensor-core pass, cached on the DeviceArray next to the float64 upload."""
     t = require_cuda()
     cached = getattr(projections, "_nps_dev32", None) if isinstance(projections, DeviceArray) else None
     if cached is not None:
         return cached
-    P32 = P64.to(t.float32).contiguous()
+    split = t.empty((2,) + tuple(P64.shape), dtype=t.float32, device=P64.device)
+    with t.cuda.device(P64.device):
+        _lib.call("nps_project_split_projections", ptr(P64), P64.shape[0], P64.shape[1], ptr(split), stream_ptr())
     norm_max = float(t.linalg.vector_norm(P64, dim=1).max().item()) * (1.0 + 1e-6)
-    out = (P32, norm_max)
+    out = (split, norm_max)
     if isinstance(projections, DeviceArray):
         projections._nps_dev32 = out
     return out
@@ -84,12 +102,14 @@ def hash_vectors(vectors, projections, return_dots=False, exact_only=False, tf32
     """Device-level hashing: vectors [N, D] -> int64 CUDA tensor [N, B/64] carrying the uint64
     signatures (bit j = (projections[j] . x >= 0) at word j//64, bit j%64 — lsh.py:33).
 
-    float32 vectors with D % 4 == 0 take the tensor-core path (K1T: TMA-fed tcgen05 TF32 GEMM,
-    sign/bit-pack epilogue, float64 fix-up of the few percent of pairs whose accumulator is too
-    close to zero); everything else, `return_dots` and `exact_only` take the float64 CUDA-core
-    kernel (K1a).  Both give the signatures of the reference's float64 arithmetic.
-    `tf32_raw=True` (measurement only) disables the fix-up, returning the bare TF32 signs, so that
-    the flipped-bit rate of the tensor-core arithmetic itself can be reported."""
+    float32 vectors with D % 4 == 0 take the tensor-core path (K1T: TMA-fed tcgen05 GEMM on
+    two-term TF32 splits of both operands, sign/bit-pack epilogue, float64 fix-up of the ~0.1 % of
+    pairs whose accumulator is too close to zero); everything else, `return_dots` and
+    `exact_only` take the float64 CUDA-core kernel (K1a).  Both give the signatures of the
+    reference's float64 arithmetic.  The call is asynchronous (no host sync).
+    `tf32_raw=True` (measurement only) disables the fix-up, returning the bare tensor-core signs,
+    so that the flipped-bit rate of the tensor-core arithmetic itself can be reported."""
+    global _last_hash_ws
     t = require_cuda()
     P = _projections_device(projections)
     X = _vectors_device(vectors)
@@ -105,21 +125,18 @@ def hash_vectors(vectors, projections, return_dots=False, exact_only=False, tf32
     with t.cuda.device(P.device):
         if (X.dtype == t.float32 and not return_dots and not exact_only and n > 0 and d % 4 == 0 and b <= 65536
                 and X.data_ptr() % 16 == 0):
-            P32, norm_max = _projections_f32(projections, P)
+            split, norm_max = _projections_split(projections, P)
             ws_bytes = _lib.raw("nps_project_sign_pack_workspace_bytes")(n, b)
             ws = t.empty(ws_bytes, dtype=t.uint8, device=P.device)
-            _lib.call("nps_project_sign_pack", ptr(X), n, d, ptr(P32), ptr(P), b, 1e-30 if tf32_raw else norm_max,
+            _lib.call("nps_project_sign_pack", ptr(X), n, d, ptr(split), ptr(P), b, 1e-30 if tf32_raw else norm_max,
                       ptr(out), ptr(ws), ws_bytes, stream_ptr())
-            import ctypes
-            fixed, cap = ctypes.c_uint32(0), ctypes.c_uint32(0)
-            _lib.call("nps_project_sign_pack_stats", ptr(ws), n, b, stream_ptr(), ctypes.byref(fixed), ctypes.byref(cap))
-            last_hash_stats.update(path="tf32+fixup", pairs=n * b, recomputed=int(fixed.value))
-            if fixed.value <= cap.value:
-                return out
-            # fix-up list overflowed (degenerate input, e.g. vectors orthogonal to everything): redo exactly
+            _last_hash_ws = (ws, n, b)
+            last_hash_stats.update(path="tf32x3+fixup", pairs=n * b, recomputed=None)
+            return out
         dots = t.empty((n, b), dtype=t.float64, device=P.device) if return_dots else None
         _lib.call("nps_project_sign_pack_f64", ptr(X), int(X.dtype == t.float32), n, d, ptr(P), b, ptr(out), ptr(dots),
                   stream_ptr())
+        _last_hash_ws = None
         last_hash_stats.update(path="f64", pairs=n * b, recomputed=n * b)
     return (out, dots) if return_dots else out
 

@@ -17,7 +17,7 @@ def run(n, d, b, seed=0):
     torch.cuda.synchronize()
     got = lsh.hash_vectors(Xd, W)
     torch.cuda.synchronize()
-    st = dict(lsh.last_hash_stats)
+    st = lsh.hash_stats()
     diff = (ref ^ got)
     nbad = int(sum(bin(int(v) & (2**64 - 1)).count("1") for v in diff.flatten().tolist())) if n * b <= 2_000_000 else int((diff != 0).sum().item())
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
