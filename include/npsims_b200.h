@@ -177,8 +177,8 @@ int nps_project_sign_pack_f64(const void *d_vectors, int vectors_are_f32, uint64
 /* K1T — the same hashing for float32 vectors on the tensor cores: TMA-fed tcgen05 kind::tf32
  * GEMM with a sign/bit-pack epilogue.  Both operands are split into two TF32 terms (x = xh + xl in
  * the kernel, w = wh + wl by nps_project_split_projections) and three products are accumulated, so
- * an accumulator is exact to (5 + dims) * 2^-22 * |x_i| * projection_norm_max; the (row,
- * projection) pairs below that (0.1 % at dims = 300) and all rows with a zero / tiny / huge /
+ * an accumulator is exact to (8 + dims / 4) * 2^-22 * |x_i| * projection_norm_max; the (row,
+ * projection) pairs below that (0.03 % at dims = 300) and all rows with a zero / tiny / huge /
  * non-finite norm are recomputed in float64 by a fix-up kernel, so the signatures equal those of
  * nps_project_sign_pack_f64.  Needs dims % 4 == 0 and 16-byte aligned inputs.
  * d_projections_split: float [2, num_projections, dims] from nps_project_split_projections (do it
