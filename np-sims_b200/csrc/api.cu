@@ -178,7 +178,12 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 // XOR+POPC streaming scan (scan.cuh).  NPS_SCAN_POPC / NPS_SCAN_MMA force one family.
 static bool choose_mma(uint64_t N, uint32_t W, uint32_t Q, uint32_t k, const DeviceInfo& dev, MmaPlan* mp) {
     if (g_scan_path == NPS_SCAN_POPC) return false;
-    if (g_scan_path == NPS_SCAN_AUTO && (Q < 64 || N < 4096)) return false;
+    // AUTO (measured, profiles/r01_c5_sweep.json): the tensor-core phases have ~0.1 ms of fixed cost
+    // (7 scan + 7 select launches); they win from 64 queries on any table worth batching, and from
+    // 16 queries once the batch holds >= 1e9 (row, query, word) triples.
+    if (g_scan_path == NPS_SCAN_AUTO &&
+        !((Q >= 64 && N >= 4096) || (Q >= 16 && (double)N * Q * W >= 1e9)))
+        return false;
     return mma_plan(N, W, Q, k, dev.sm_count, dev.smem_optin, mp);
 }
 

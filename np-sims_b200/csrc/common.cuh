@@ -117,7 +117,7 @@ __host__ __device__ constexpr int gcd_int(int a, int b) { return b == 0 ? a : gc
 
 // rows each thread keeps in registers, by signature width (64-bit words)
 __host__ __device__ constexpr int rows_per_thread(int words) {
-    return words <= 4 ? 8 : words <= 6 ? 6 : words <= 10 ? 4 : words <= 20 ? 2 : 1;
+    return words <= 4 ? 8 : words <= 6 ? 6 : words <= 8 ? 4 : words <= 20 ? 2 : 1;
 }
 
 }  // namespace nps
