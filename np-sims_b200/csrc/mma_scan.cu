@@ -46,12 +46,18 @@ __device__ __forceinline__ void expand_row_kblock(uint32_t tile_base, uint32_t r
 // tensor core: one extra K = 64 slice whose A elements are all 4.0 and whose B row n spells -T_n / 4
 // as a sum of E2M1 values, so the accumulator holds  dot - T  and the epilogue only looks at sign
 // bits.  4 * {0, .5, 1, 1.5, 2, 3, 4, 6} = {0, 2, 4, 6, 8, 12, 16, 24}: |T| / 2 = 12 * n12 + rem with
-// rem < 12 written as at most two of {1, 2, 3, 4, 6, 8}.
-__device__ __forceinline__ float clamp_thr(float t) {
-    return fminf(fmaxf(t, -(float)kMmaThrRange), (float)kMmaThrRange);   // +-inf -> never / always
+// rem < 12 written as at most two of {1, 2, 3, 4, 6, 8}.  One slice spells |T| <= 1510 (23 words);
+// wider signatures use two slices, T = T1 + T2 with |T1|, |T2| <= 1510 (thr_split).
+__device__ __forceinline__ float clamp_thr(float t, uint32_t words) {
+    const float r = words > kMmaThrOneSlice ? (float)kMmaThrRange : (float)kMmaThrSlice;
+    return fminf(fmaxf(t, -r), r);   // +-inf -> never / always
 }
-__device__ __forceinline__ void encode_thr(float t, uint32_t (&out)[8]) {
-    const int T = (int)clamp_thr(t);
+__device__ __forceinline__ void thr_split(float t, uint32_t words, int& T1, int& T2) {
+    const int T = (int)clamp_thr(t, words);
+    T1 = min(max(T, -kMmaThrSlice), kMmaThrSlice);
+    T2 = T - T1;
+}
+__device__ __forceinline__ void encode_thr(int T, uint32_t (&out)[8]) {
     const uint32_t m = (uint32_t)(T < 0 ? -T : T) >> 1;
     const int n12 = (int)(m / 12u);
     const uint32_t rem = m - 12u * (uint32_t)n12;
@@ -296,6 +302,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         const uint64_t b_desc0 = umma_desc_k_sw128(base + L.b_off);
         const uint64_t athr_desc = umma_desc_k_noswizzle(base + L.athr_off, 128u, 256u);
         const uint64_t bthr_desc = umma_desc_k_noswizzle(base + L.bthr_off, 128u, 256u);
+        const uint64_t bthr2_desc = umma_desc_k_noswizzle(base + L.bthr_off + NT * 32u, 128u, 256u);
         uint32_t t_idx = 0, it_idx = 0, lg = 0;   // lg: groups consumed by this issuer
         for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x, ++it_idx) {
             const uint32_t chunk = item / p.num_qtiles;
@@ -330,7 +337,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                         }
                         umma_commit(&g_empty[slot]);                  // group reusable once these MMAs retire
                         if (g + 1 == GPT) {
-                            if (!p.dense) umma_mxf4(d_tmem, athr_desc, bthr_desc, idesc, sfa, sfb, 1u);   // ... - T
+                            if (!p.dense) {                                                                // ... - T
+                                umma_mxf4(d_tmem, athr_desc, bthr_desc, idesc, sfa, sfb, 1u);
+                                if (W > kMmaThrOneSlice) umma_mxf4(d_tmem, athr_desc, bthr2_desc, idesc, sfa, sfb, 1u);
+                            }
                             umma_commit(&acc_full[buf]);              // accumulator complete -> epilogue
                         }
                     }
@@ -378,10 +388,17 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
             if (!p.dense && part == 0) {
                 for (uint32_t n = u; n < NT; n += kMmaTileRows) {
                     uint32_t e[8];
-                    encode_thr(__ldg(p.thrT + q0 + n), e);
+                    int T1, T2;
+                    thr_split(__ldg(p.thrT + q0 + n), W, T1, T2);
+                    encode_thr(T1, e);
                     const uint32_t dst = base + L.bthr_off + (n >> 3) * 256u + (n & 7u) * 16u;
                     sts128(dst, e[0], e[1], e[2], e[3]);
                     sts128(dst + 128u, e[4], e[5], e[6], e[7]);
+                    if (W > kMmaThrOneSlice) {   // second slice
+                        encode_thr(T2, e);
+                        sts128(dst + NT * 32u, e[0], e[1], e[2], e[3]);
+                        sts128(dst + NT * 32u + 128u, e[4], e[5], e[6], e[7]);
+                    }
                 }
             }
             fence_proxy_async_smem();
@@ -465,7 +482,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
             const uint32_t i1 = min(i0 + p.tiles_per_chunk, p.phase_tiles);
             if constexpr (!kDense) {   // this warp's thresholds for the item's query tile
                 __syncwarp();
-                for (uint32_t c = lane; c < cpw; c += 32u) thr_s[c] = clamp_thr(__ldg(p.thrT + q0 + c));
+                for (uint32_t c = lane; c < cpw; c += 32u) thr_s[c] = clamp_thr(__ldg(p.thrT + q0 + c), W);
                 __syncwarp();
             }
             for (uint32_t i = i0; i < i1; ++i, ++t_idx) {

@@ -44,8 +44,10 @@ constexpr uint32_t kMmaSfCol = 448;       // TMEM columns [448, 512): block scal
 constexpr uint32_t kMmaMaxNTile = 224;    // 2 accumulators x 224 columns = 448
 constexpr int kMmaAStageBytes = kMmaTileRows * kMmaKBlockBytes;   // 16 KB
 constexpr int kMmaHitsPerWarp = 64;
-constexpr uint32_t kMmaMaxWords = 23;      // |dot - threshold| must stay inside the folded-threshold range
-constexpr int kMmaThrRange = 1510;         // thresholds are clamped to +-this (even); > 64 * 23 bits
+constexpr uint32_t kMmaMaxWords = 40;      // 2560 bits (the widest signatures the reference benchmarks)
+constexpr uint32_t kMmaThrOneSlice = 23;   // up to here ONE folded-threshold slice covers |threshold| <= 64 * words
+constexpr int kMmaThrSlice = 1510;         // what one K = 64 threshold slice can spell (even; 64 * 6 * 4 = 1536 max)
+constexpr int kMmaThrRange = 2 * kMmaThrSlice;   // thresholds are clamped to +-this; > 64 * 40 bits
 
 struct MmaScanParams {
     const uint64_t* hashes;    // [N, W] bit-packed
@@ -83,8 +85,8 @@ __host__ __device__ inline MmaSmem mma_smem_layout(uint32_t words, uint32_t n_ti
     off += a_stages * kMmaAStageBytes;
     s.athr_off = off;   // threshold operand tiles (no-swizzle K-major, one K = 64 slice): A = 4.0 everywhere,
     off += kMmaTileRows * 32;
-    s.bthr_off = off;   // B row n = -(threshold of query n) / 4 spelled in E2M1 elements
-    off += n_tile * 32;
+    s.bthr_off = off;   // B row n = -(threshold of query n) / 4 spelled in E2M1 elements; a second tile
+    off += n_tile * 32 * (words > kMmaThrOneSlice ? 2u : 1u);   // (second slice) for wide signatures
     s.p_off = off;
     s.p_stride = (kMmaTileRows * words * 8 + 127u) & ~127u;
     off += p_stages * s.p_stride;

@@ -2,7 +2,7 @@
 
 The tcgen05 kind::mxf4 path must return bit-identical ids and distances to the oracle's canonical
 order (ascending (distance, row id)) and to the XOR+POPC scan on the same inputs: every width up
-to 23 words, ragged row/query counts, heavy ties, duplicate rows, sorted ("adversarial") row
+to 40 words (two folded-threshold slices from 24), ragged row/query counts, heavy ties, duplicate rows, sorted ("adversarial") row
 orders that overflow the candidate buffers, k from 1 to 1000, shard offsets."""
 import numpy as np
 import pytest
@@ -48,7 +48,7 @@ def check_against_oracle(nps, h, q, k, queries):
     return rows, dists
 
 
-@pytest.mark.parametrize("w", [1, 2, 3, 4, 5, 7, 8, 9, 10, 12, 13, 16, 17, 20, 23])
+@pytest.mark.parametrize("w", [1, 2, 3, 4, 5, 7, 8, 9, 10, 12, 13, 16, 17, 20, 23, 24, 25, 32, 33, 40])
 def test_mma_all_widths_vs_oracle(nps, force_mma, w):
     rng = np.random.default_rng(100 + w)
     n = int(rng.integers(3000, 20000))
@@ -91,6 +91,27 @@ def test_mma_equals_popc_scan_bitwise(nps, force_mma):
     r0, d0 = nps.hamming_top_n(H, Q, 100, return_distances=True)
     assert force_mma.raw("nps_last_scan_path")() == force_mma.SCAN_POPC
     assert torch.equal(r0, r1) and torch.equal(d0, d1)
+
+
+@pytest.mark.parametrize("w,k", [(32, 10), (40, 100)])
+def test_mma_wide_signatures_equal_popc_scan(nps, force_mma, w, k):
+    # 2048 / 2560-bit signatures: two folded-threshold slices, narrow query tiles; far and near rows mixed
+    import torch
+    rng = np.random.default_rng(w)
+    h = rand_sigs(rng, 60_000, w)
+    q = rand_sigs(rng, 300, w)
+    q[:100] = h[rng.integers(0, len(h), size=100)]
+    q[:50, ::3] ^= np.uint64(0xF0F0)
+    h[1000:1100] = ~q[7]                                          # rows at (almost) the maximum distance
+    H, Q = torch.from_numpy(h.view(np.int64)).cuda(), torch.from_numpy(q.view(np.int64)).cuda()
+    r1, d1 = nps.hamming_top_n(H, Q, k, return_distances=True)
+    assert force_mma.raw("nps_last_scan_path")() == force_mma.SCAN_MMA
+    force_mma.set_scan_path(force_mma.SCAN_POPC)
+    r0, d0 = nps.hamming_top_n(H, Q, k, return_distances=True)
+    assert force_mma.raw("nps_last_scan_path")() == force_mma.SCAN_POPC
+    assert torch.equal(r0, r1) and torch.equal(d0, d1)
+    want_r, want_d = oracle.top_k_canonical(h, q[7], k)
+    assert np.array_equal(r1[7].cpu().numpy().view(np.uint64), want_r)
 
 
 def test_mma_duplicates_and_index_ties(nps, force_mma):
