@@ -174,6 +174,15 @@ int nps_project_sign_pack_f64(const void *d_vectors, int vectors_are_f32, uint64
                               uint32_t dims, const double *d_projections, uint32_t num_projections,
                               uint64_t *d_out, double *d_dots, void *stream);
 
+/* K6 — second phase of the two-phase search (lsh.py:84-91: `hashes[candidates]` gathered, then
+ * hamming_top_10 on the copy, then `candidates[best]`): for every query the k candidates with the
+ * smallest FULL-width distance, ascending (distance, row id), reading the candidate rows in place.
+ * d_candidates [num_queries, num_candidates] global row ids (e.g. nps_hamming_top_n on the front
+ * words); ids of UINT64_MAX or >= num_hashes are ignored; num_candidates <= 4096. */
+int nps_rerank_top_n(const uint64_t *d_hashes, uint64_t num_hashes, uint32_t words, const uint64_t *d_queries,
+                     uint32_t num_queries, const uint64_t *d_candidates, uint32_t num_candidates, uint32_t k,
+                     uint64_t *d_out_rows, uint64_t *d_out_dists, void *stream);
+
 /* K1T — the same hashing for float32 vectors on the tensor cores: TMA-fed tcgen05 kind::tf32
  * GEMM with a sign/bit-pack epilogue.  Both operands are split into two TF32 terms (x = xh + xl in
  * the kernel, w = wh + wl by nps_project_split_projections) and three products are accumulated, so

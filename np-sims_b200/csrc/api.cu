@@ -13,6 +13,7 @@
 #include "mma_scan.cuh"
 #include "project.cuh"
 #include "replay.cuh"
+#include "rerank.cuh"
 #include "scan.cuh"
 
 namespace nps {
@@ -521,6 +522,20 @@ int nps_num_unshared_bits(const uint64_t* d_a, uint64_t len_a, const uint64_t* d
     int rc = device_info(&dev);
     if (rc) return rc;
     NPS_CUDA(launch_unshared_bits(d_a, len_a, d_b, len_b, n, d_out, dev.sm_count, (cudaStream_t)stream));
+    return NPS_OK;
+}
+
+int nps_rerank_top_n(const uint64_t* d_hashes, uint64_t num_hashes, uint32_t words, const uint64_t* d_queries,
+                     uint32_t num_queries, const uint64_t* d_candidates, uint32_t num_candidates, uint32_t k,
+                     uint64_t* d_out_rows, uint64_t* d_out_dists, void* stream) {
+    if (words == 0 || words > NPS_MAX_WORDS) return fail(NPS_EINVAL, "words=%u outside [1, %u]", words, NPS_MAX_WORDS);
+    if (k == 0 || k > NPS_MAX_K) return fail(NPS_EINVAL, "k=%u outside [1, %u]", k, NPS_MAX_K);
+    if (num_candidates == 0 || num_candidates > 4096) return fail(NPS_EINVAL, "num_candidates=%u outside [1, 4096]", num_candidates);
+    if (num_queries == 0) return NPS_OK;
+    if (!d_hashes || !d_queries || !d_candidates || !d_out_rows) return fail(NPS_EINVAL, "null pointer");
+    if (reinterpret_cast<uintptr_t>(d_hashes) & 15u) return fail(NPS_EINVAL, "d_hashes must be 16-byte aligned");
+    NPS_CUDA(launch_rerank(d_hashes, num_hashes, words, d_queries, num_queries, d_candidates, num_candidates, k,
+                           d_out_rows, d_out_dists, (cudaStream_t)stream));
     return NPS_OK;
 }
 

@@ -9,8 +9,9 @@ from np_sims.ufuncs import hamming as hamming_c
 from np_sims.ufuncs import hamming_top_10
 from np_sims.ufuncs import hamming_top_cand
 from np_sims.ufuncs import hamming_top_n
+from np_sims.ufuncs import hamming_rerank
 
 from np_sims.hamming import hamming_naive
 
 __all__ = ["num_unshared_bits", "hamming_c", "hamming_top_10", "hamming_top_cand", "hamming_top_n",
-           "hamming_naive"]
+           "hamming_rerank", "hamming_naive"]

@@ -54,6 +54,7 @@ _SIGS = {
     "nps_hamming_top_n_reference_workspace_bytes": (_sz, [_u64, _u32, _u32]),
     "nps_hamming_top_n_reference": (_int, [_vp, _u64, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _sz, _vp]),
     "nps_num_unshared_bits": (_int, [_vp, _u64, _vp, _u64, _u64, _vp, _vp]),
+    "nps_rerank_top_n": (_int, [_vp, _u64, _u32, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp]),
     "nps_project_sign_pack_workspace_bytes": (_sz, [_u64, _u32]),
     "nps_project_split_projections": (_int, [_vp, _u32, _u32, _vp, _vp]),
     "nps_project_sign_pack": (_int, [_vp, _u64, _u32, _vp, _vp, _u32, ctypes.c_float, _vp, _vp, _sz, _vp]),

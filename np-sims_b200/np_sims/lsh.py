@@ -233,6 +233,31 @@ query = query_with_hamming_top_n  # Default query to fastest
 query_two_phase = query_with_hamming_top_n_two_phase
 
 
+def query_two_phase_batch(vectors, front_hashes, hashes, projections, n=10, num_candidates=1000,
+                          return_distances=False):
+    """Not in the reference as a batch: its two-phase recipe (lsh.py:84-91, the fastest-recall
+    configuration of benchmark/glove.py) for a whole batch of query vectors, fused on the device —
+    K1 hashes the batch, the batched scan (K2T/K2) takes the `num_candidates` best rows on the
+    FRONT words, K6 re-ranks them on the full signatures in place (no gathered copy) — in
+    canonical order at both stages (ascending (distance, row id)).  `query_two_phase` remains the
+    single-query, reference-queue-order form."""
+    sigs = hash_vectors(vectors, projections)
+    t = require_cuda()
+    from ._device import u64_table
+    F, _ = u64_table(front_hashes, "query_two_phase_batch", ndim=2)
+    front_sigs = sigs[:, :F.shape[1]].contiguous()
+    cand = hamming_top_n(F, front_sigs, n=int(num_candidates))
+    from np_sims.ufuncs import hamming_rerank
+    H, _ = u64_table(hashes, "query_two_phase_batch", ndim=2)
+    out = hamming_rerank(H, sigs, cand, n=n, return_distances=return_distances)
+    if is_tensor(vectors) or is_tensor(hashes):
+        return out
+
+    def host(x):
+        return x.cpu().numpy().view(np.uint64) if is_tensor(x) else x
+    return tuple(host(o) for o in out) if return_distances else host(out)
+
+
 # ------------------------------------------------------------------------------- batched API
 def query_batch(vectors, hashes, projections, n=10, return_distances=False):
     """Not in the reference: hash a batch of query vectors (K1) and search them in one fused

@@ -118,6 +118,34 @@ def hamming_top_n(hashes, query, n=10, return_distances=False, order="canonical"
     return _finish(rows, single, host)
 
 
+def hamming_rerank(hashes, query, candidates, n=10, return_distances=False):
+    """Second phase of the two-phase search (lsh.py:88-91): of each query's `candidates` (row ids
+    `[c]` / `[q, c]`, e.g. `hamming_top_n` on the front words) the n with the smallest FULL-width
+    distance, ascending (distance, row id).  The candidate rows are read in place (K6,
+    rerank.cu) — no gathered copy of the table.  Ids of UINT64_MAX or beyond the table are ignored."""
+    t = require_cuda()
+    n = int(n)
+    if not 1 <= n <= _lib.NPS_MAX_K:
+        raise ValueError(f"n={n} outside [1, {_lib.NPS_MAX_K}]")
+    H, Q, single, host = _prepare(hashes, query, "hamming_rerank")
+    C, c_host = u64_table(candidates, "hamming_rerank")
+    if C.dim() == 1:
+        C = C.reshape(1, -1)
+    if C.dim() != 2 or C.shape[0] != Q.shape[0] or not 1 <= C.shape[1] <= 4096:
+        raise ValueError(f"hamming_rerank: candidates must be [q, c] with c <= 4096, got {tuple(C.shape)}")
+    C = C.to(H.device).contiguous()
+    host = host and not is_tensor(candidates)
+    q = Q.shape[0]
+    rows = t.empty((q, n), dtype=t.int64, device=H.device)
+    dists = t.empty((q, n), dtype=t.int64, device=H.device) if return_distances else None
+    with t.cuda.device(H.device):
+        _lib.call("nps_rerank_top_n", ptr(H), H.shape[0], H.shape[1], ptr(Q), q, ptr(C), C.shape[1], n, ptr(rows),
+                  ptr(dists), stream_ptr())
+    if return_distances:
+        return _finish(rows, single, host), _finish(dists, single, host)
+    return _finish(rows, single, host)
+
+
 _last_ws = None
 
 

@@ -269,3 +269,20 @@ def two_phase(hashes, query, front_words: int, cand: int = 1000, k: int = 10) ->
     out = np.empty(k, dtype=np.uint64)
     lib().orc_two_phase(_p(h), _p(q), h.shape[0], h.shape[1], front_words, cand, k, _p(out))
     return out
+
+
+def two_phase_canonical(hashes, query, front_words: int, cand: int = 1000, k: int = 10):
+    """np_sims/lsh.py:84-91 with the canonical tie rule at BOTH selections (the batched
+    `lsh.query_two_phase_batch`): candidates = the `cand` rows with the smallest distance on the
+    first `front_words` words, ties by lowest row id; result = the k candidates with the smallest
+    full-width distance, ties by lowest row id.  -> (rows, dists), UINT64_MAX padded."""
+    h, q = _u64c(hashes), _u64c(query)
+    front = hamming_np(np.ascontiguousarray(h[:, :front_words]), q[:front_words])
+    c = np.argsort(front, kind="stable")[:cand]
+    full = hamming_np(h[c], q)
+    order = np.lexsort((c, full))[:k]
+    rows = np.full(k, np.iinfo(np.uint64).max, dtype=np.uint64)
+    dists = np.full(k, np.iinfo(np.uint64).max, dtype=np.uint64)
+    rows[:len(order)] = c[order].astype(np.uint64)
+    dists[:len(order)] = full[order].astype(np.uint64)
+    return rows, dists

@@ -438,3 +438,43 @@ def test_merge_more_than_65535_queries(nps):
     want = np.sort(np.transpose(keys, (1, 0, 2)).reshape(q, -1), axis=1)[:, :k]
     assert np.array_equal(rows.cpu().numpy().view(np.uint64), want & np.uint64((1 << 40) - 1))
     assert np.array_equal(dists.cpu().numpy().view(np.uint64), want >> np.uint64(40))
+
+
+# ------------------------------------------------------------------------------ K6 two-phase, batched
+def test_rerank_and_batched_two_phase_equal_oracle(nps, c1_glove):
+    """lsh.py:84-91 as a batch: front-word top-1000 (canonical) -> K6 re-rank in place == the
+    NumPy restatement, on the reference's glove sample and on random signatures with padding."""
+    import torch
+    import np_sims.lsh as lsh
+    H = c1_glove["H"]
+    q_ids = c1_glove["q_ids"]
+    front = np.ascontiguousarray(H[:, :2])
+    cand = nps.hamming_top_n(front, np.ascontiguousarray(H[q_ids][:, :2]), 1000)
+    rows, dists = nps.hamming_rerank(H, H[q_ids], cand, 10, return_distances=True)
+    for j, qi in enumerate(q_ids):
+        want_r, want_d = oracle.two_phase_canonical(H, H[qi], 2, 1000, 10)
+        assert np.array_equal(rows[j], want_r) and np.array_equal(dists[j], want_d)
+        full = oracle.hamming(H, H[qi])                    # same distances as the reference's two-phase
+        assert np.array_equal(np.sort(full[c1_glove["ref_two_phase"][j].astype(np.int64)]), dists[j])
+    # vectors in, ids out (hash -> front scan -> re-rank), batch of 200 queries, tensor-core scan
+    X = c1_glove["X"]
+    np.random.seed(0)
+    W = lsh.create_projections(640, 300)
+    got = lsh.query_two_phase_batch(X[:200], front, H, W, n=10, num_candidates=1000)
+    sig = oracle.index_np(X[:200], np.asarray(W))
+    for i in (0, 7, 199):
+        assert np.array_equal(got[i], oracle.two_phase_canonical(H, sig[i], 2, 1000, 10)[0])
+    # fewer rows than candidates (padding ids), odd width, k > rows
+    rng = np.random.default_rng(81)
+    h = rand_sigs(rng, 37, 3)
+    q = rand_sigs(rng, 5, 3)
+    cand = nps.hamming_top_n(np.ascontiguousarray(h[:, :1]), np.ascontiguousarray(q[:, :1]), 64)
+    assert cand[0, 37] == np.iinfo(np.uint64).max
+    rows, dists = nps.hamming_rerank(h, q, cand, 40, return_distances=True)
+    for i in range(5):
+        want_r, want_d = oracle.two_phase_canonical(h, q[i], 1, 64, 40)
+        assert np.array_equal(rows[i], want_r) and np.array_equal(dists[i], want_d)
+    # device tensors stay on the device
+    out = nps.hamming_rerank(torch.from_numpy(h.view(np.int64)).cuda(), torch.from_numpy(q.view(np.int64)).cuda(),
+                             torch.from_numpy(cand.view(np.int64)).cuda(), 10)
+    assert out.is_cuda and np.array_equal(out.cpu().numpy().view(np.uint64), rows[:, :10])

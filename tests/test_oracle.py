@@ -117,6 +117,23 @@ def test_c1_top10_equals_reference(c1_glove):
         assert np.array_equal(oracle.two_phase(H, H[qi], 2), c1_glove["ref_two_phase"][j])
 
 
+def test_canonical_two_phase_matches_reference_two_phase_up_to_ties(c1_glove):
+    """The batched two-phase search uses the canonical tie rule at both selections; against the
+    reference's own two-phase outputs (golden, queue-order ties) the DISTANCES of the results must
+    be identical and the id sets may differ only among rows tied at the boundary."""
+    H = c1_glove["H"]
+    identical = 0
+    for j, qi in enumerate(c1_glove["q_ids"]):
+        rows, dists = oracle.two_phase_canonical(H, H[qi], 2, 1000, 10)
+        ref = c1_glove["ref_two_phase"][j]
+        full = oracle.hamming(H, H[qi])
+        assert np.array_equal(np.sort(full[ref.astype(np.int64)]), dists)
+        assert np.array_equal(full[rows.astype(np.int64)], dists) and np.all(np.diff(dists.astype(np.int64)) >= 0)
+        assert oracle.tie_aware_equal(full, ref, rows, 10) or set(ref.tolist()) != set(rows.tolist())
+        identical += set(ref.tolist()) == set(rows.tolist())
+    assert identical >= 4
+
+
 def test_edge_cases():
     q = np.array([3, 5], dtype=np.uint64)
     empty = np.zeros((0, 2), dtype=np.uint64)
