@@ -2,6 +2,7 @@
 (through the np_sims drop-in surface or the C ABI) with the oracle / the reference's golden
 vectors on the same inputs.  Integer work is compared bit for bit."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -478,3 +479,29 @@ def test_rerank_and_batched_two_phase_equal_oracle(nps, c1_glove):
     out = nps.hamming_rerank(torch.from_numpy(h.view(np.int64)).cuda(), torch.from_numpy(q.view(np.int64)).cuda(),
                              torch.from_numpy(cand.view(np.int64)).cuda(), 10)
     assert out.is_cuda and np.array_equal(out.cpu().numpy().view(np.uint64), rows[:, :10])
+
+
+def test_recall_harness_index_files_use_the_reference_format(nps, tmp_path, monkeypatch):
+    """benchmark/recall.py caches the index under the reference's file names and formats
+    (benchmark/glove.py:262-279): np.save of uint64 [N, B/64] and float64 [B, D]."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "recall_harness", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmark", "recall.py"))
+    rec = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rec)
+    monkeypatch.setattr(rec, "DATA_PATH", str(tmp_path) + "/")
+    x = rec.synthetic_vectors(700, 64, 20, 3)
+    q, ix = rec.test_train_split(x, 50, np.random.default_rng(0))
+    assert q.shape == (50, 64) and ix.shape == (650, 64)
+    hashes, projs, _ = rec.load_or_build_index(ix, 128, 0)
+    hf, pf = tmp_path / "hashes_650_128_64_0.npy", tmp_path / "projs_650_128_64_0.npy"
+    assert hf.exists() and pf.exists()
+    h2, p2, _ = rec.load_or_build_index(ix, 128, 0)                     # second call loads the files
+    assert h2.dtype == np.uint64 and h2.shape == (650, 2) and p2.dtype == np.float64 and p2.shape == (128, 64)
+    assert np.array_equal(h2, np.asarray(hashes)) and np.array_equal(h2, oracle.index_np(ix, p2))
+    gt = rec.most_similar_cos(ix, q)
+    ids, _ = rec.run_algorithm("lsh_batch", q, h2, p2, None)
+    assert ids.shape == (50, 10) and 0.0 <= rec.recall_at_10(ids, gt) <= 1.0
+    one, _ = rec.run_algorithm("lsh_pure_c", q[:3], h2, p2, None)
+    full = oracle.hamming(h2, oracle.index_np(q[:1], p2)[0])
+    assert oracle.tie_aware_equal(full, one[0], ids[0], 10)
