@@ -12,9 +12,10 @@
 //   * each thread tests its 8 (or 4) consecutive distances against the worst distance at
 //     tile start (the worst only ever decreases, so this is a superset filter) — one
 //     __syncthreads_or per tile decides "nothing to do", the steady state;
-//   * tiles that do contain candidates hand them, in row order, to warp 0, which re-tests
-//     each against the live worst, writes the slot, and rescans the k slots for the first
-//     maximum with a warp max-reduce over (distance, -slot).
+//   * tiles that do contain candidates hand them, in row order, to warp 0, which re-filters
+//     each group of 32 threads against the live worst in parallel, re-tests the survivors one
+//     by one, writes the slot, and rescans the k slots for the first maximum with a warp
+//     max-reduce over (distance, -slot).
 //
 // No host replay, no CPU fallback: the whole queue lives in shared memory.
 #include "common.cuh"
@@ -52,12 +53,20 @@ __global__ void __launch_bounds__(kReplayThreads, 1) replay_queue_kernel(const D
     }
     __syncthreads();
 
-    auto rescan = [&]() {   // warp 0: first slot holding the maximum (ufunc.c:163-169)
+    // warp 0: first slot holding the maximum (ufunc.c:163-169).  Lane l owns slots l, l + 32, ... and
+    // caches the maximum over them, so an insert costs one re-scan of the OWNER's k/32 slots plus a
+    // warp max-reduce, not a pass over all k slots (k = 1000: ~150 instead of ~600 cycles).
+    uint64_t lane_best = 0;
+    auto rescan_lane = [&]() {
         uint64_t best = 0;
         for (uint32_t i = lane; i < k; i += 32) {
-            const uint64_t key = ((uint64_t)slot_score[i] << 32) | (0xFFFFFFFFu - i);
+            const uint64_t key = ((uint64_t)((volatile uint32_t*)slot_score)[i] << 32) | (0xFFFFFFFFu - i);
             best = key > best ? key : best;
         }
+        lane_best = best;
+    };
+    auto publish_worst = [&]() {
+        uint64_t best = lane_best;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
@@ -71,7 +80,10 @@ __global__ void __launch_bounds__(kReplayThreads, 1) replay_queue_kernel(const D
     };
 
     if (N > k && k > 0) {
-        if (warp == 0) rescan();
+        if (warp == 0) {
+            rescan_lane();
+            publish_worst();
+        }
         __syncthreads();
 
         const unsigned long long first = k;                       // sequential part starts at row k
@@ -129,7 +141,21 @@ __global__ void __launch_bounds__(kReplayThreads, 1) replay_queue_kernel(const D
                     // element order inside the tile: vector j (outer), thread, element x
                     for (int j = 0; j < kReplayVecs; ++j) {
                         for (int t0 = 0; t0 < kReplayThreads; t0 += 32) {
-                            const uint32_t f = (flags[t0 + lane] >> (j * EPV)) & ((1u << EPV) - 1u);
+                            uint32_t f = (flags[t0 + lane] >> (j * EPV)) & ((1u << EPV) - 1u);
+                            if (f) {
+                                // Re-filter against the LIVE worst (it only decreases) before walking the group
+                                // in row order: the tile-start filter lets half of the first tile through, and
+                                // every candidate costs ~250 cycles of serial work on this warp.
+                                const uint32_t w = *reinterpret_cast<volatile uint32_t*>(&worst_s);
+                                const uint4 v = *reinterpret_cast<const uint4*>(
+                                    &tile_s[((size_t)j * kReplayThreads + t0 + lane) * EPV]);
+                                const DistT* e = reinterpret_cast<const DistT*>(&v);
+                                uint32_t g = 0;
+#pragma unroll
+                                for (int x = 0; x < EPV; ++x)
+                                    if ((uint32_t)e[x] < w) g |= 1u << x;
+                                f &= g;
+                            }
                             uint32_t any = __ballot_sync(0xffffffffu, f != 0);
                             while (any) {
                                 const int src = __ffs(any) - 1;
@@ -140,14 +166,16 @@ __global__ void __launch_bounds__(kReplayThreads, 1) replay_queue_kernel(const D
                                     fm &= fm - 1;
                                     const uint32_t off = ((uint32_t)j * kReplayThreads + t0 + src) * EPV + x;
                                     const uint32_t score = (uint32_t)tile_s[off];
-                                    if (score < worst_s) {   // ufunc.c:152, live worst
+                                    if (score < *reinterpret_cast<volatile uint32_t*>(&worst_s)) {   // ufunc.c:152, live worst
+                                        const uint32_t slot = *reinterpret_cast<volatile uint32_t*>(&worst_slot_s);
+                                        __syncwarp();
                                         if (lane == 0) {
-                                            const uint32_t slot = worst_slot_s;
                                             slot_score[slot] = score;
                                             slot_row[slot] = base + off;
                                         }
                                         __syncwarp();
-                                        rescan();
+                                        if ((slot & 31u) == (uint32_t)lane) rescan_lane();
+                                        publish_worst();
                                     }
                                 }
                             }
