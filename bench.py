@@ -342,7 +342,7 @@ def run_b200(args, wl):
         if _lib.raw("nps_last_scan_path")() == _lib.SCAN_MMA:
             phase_runs.append(_lib.profile_last_phases())
     _lib.raw("nps_profile_enable")(0)
-    scan_avg = float(np.mean(scan_ms))
+    scan_avg = float(np.median(scan_ms))
     n_local = b[rank + 1] - b[rank]
     nq_local = qhi - qlo
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max_mhz
@@ -358,7 +358,7 @@ def run_b200(args, wl):
         tensor_peak = 4.0 * bf16_peak
         nph = len(phase_runs[0])
         tiles = [phase_runs[0][j][0] for j in range(nph)]
-        ph_ms = [float(np.mean([r[j][1] for r in phase_runs])) for j in range(nph)]
+        ph_ms = [float(np.median([r[j][1] for r in phase_runs])) for j in range(nph)]
         dom = int(np.argmax(ph_ms))
         rows_dom = min(tiles[dom] * 128, n_local)
         flop_dom = 2.0 * rows_dom * nq_local * wl["bits"]

@@ -24,7 +24,7 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* a, uint32_t 
 
 // in : [Q, lists_in, k]   out_keys: [Q, lists_out, k]  (lists_out = ceil(lists_in / G))
 // final pass (out_rows != nullptr, lists_out == 1): rows [Q,k] u64, dists [Q,k] u64 (may be null)
-__global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __restrict__ in, uint32_t lists_in,
+__global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __restrict__ in, uint32_t Q, uint32_t lists_in,
                                                           size_t q_stride, size_t list_stride,
                                                           uint32_t k, uint32_t G, uint64_t* __restrict__ out_keys,
                                                           uint64_t* __restrict__ out_rows,
@@ -32,11 +32,14 @@ __global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __rest
                                                           const uint32_t* __restrict__ gate) {
     if (gate != nullptr && *gate == 0u) return;   // gated repair launch (api.cu), nothing to repair
     extern __shared__ __align__(16) uint64_t skeys[];
-    const uint32_t q = blockIdx.x, grp = blockIdx.y, lists_out = gridDim.y;   // queries on x: up to 2^31-1
+    const uint32_t grp = blockIdx.y, lists_out = gridDim.y;
     const uint32_t g0 = grp * G;
     const uint32_t g = (lists_in - g0) < G ? (lists_in - g0) : G;
     const uint32_t n = g * k;
+    // queries on x, grid-stride (gated launches use a small grid so that a no-op costs ~2 us)
+    for (uint32_t q = blockIdx.x; q < Q; q += gridDim.x) {
     const uint64_t* src = in + (size_t)q * q_stride + (size_t)g0 * list_stride;
+    __syncthreads();
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t a = i / k;
         skeys[i] = src[(size_t)a * list_stride + (i - a * k)];
@@ -58,6 +61,7 @@ __global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __rest
             }
         }
     }
+    }
 }
 
 // Few short lists (the single-query / small-batch scan: ~148 lists of k <= 64 keys): the rank merge
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__(256) merge_lists_kernel(const uint64_t* __rest
 // "smallest key greater than the previous winner" (keys are unique): k rounds of a strided scan +
 // shuffle/shared-memory min — ~150 cycles per round.
 constexpr uint32_t kSmallMergeKeys = 4096, kSmallMergeK = 64;
-__global__ void __launch_bounds__(256) merge_small_kernel(const uint64_t* __restrict__ in, uint32_t lists,
+__global__ void __launch_bounds__(256) merge_small_kernel(const uint64_t* __restrict__ in, uint32_t Q, uint32_t lists,
                                                           size_t q_stride, size_t list_stride, uint32_t k,
                                                           uint64_t* __restrict__ out_keys,
                                                           uint64_t* __restrict__ out_rows,
@@ -75,8 +79,10 @@ __global__ void __launch_bounds__(256) merge_small_kernel(const uint64_t* __rest
     if (gate != nullptr && *gate == 0u) return;
     __shared__ uint64_t skeys[kSmallMergeKeys];
     __shared__ uint64_t wmin[8];
-    const uint32_t q = blockIdx.x, n = lists * k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = lists * k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t q = blockIdx.x; q < Q; q += gridDim.x) {
     const uint64_t* src = in + (size_t)q * q_stride;
+    __syncthreads();
     for (uint32_t i = tid; i < n; i += 256) {
         const uint32_t a = i / k;
         skeys[i] = src[(size_t)a * list_stride + (i - a * k)];
@@ -113,6 +119,7 @@ __global__ void __launch_bounds__(256) merge_small_kernel(const uint64_t* __rest
         prev = best;          // kNone from here on: nothing is > kNone, every later slot is a pad
         first = false;
     }
+    }
 }
 
 uint32_t merge_group_size(uint32_t k) {
@@ -134,13 +141,14 @@ cudaError_t launch_merge(const uint64_t* keys, uint32_t Q, uint32_t lists, uint3
                          cudaStream_t stream, const uint32_t* gate) {
     if (Q == 0 || k == 0) return cudaSuccess;
     if (k <= kSmallMergeK && (uint64_t)lists * k <= kSmallMergeKeys && lists > 1) {
-        merge_small_kernel<<<Q, 256, 0, stream>>>(keys, lists, list_major ? (size_t)k : (size_t)lists * k,
+        merge_small_kernel<<<gate ? (Q < 592u ? Q : 592u) : Q, 256, 0, stream>>>(keys, Q, lists, list_major ? (size_t)k : (size_t)lists * k,
                                                   list_major ? (size_t)Q * k : (size_t)k, k, out_keys,
                                                   out_keys ? nullptr : out_rows, out_keys ? nullptr : out_dists, gate);
         count_launch();
         return cudaGetLastError();
     }
     const uint32_t G = merge_group_size(k);
+    const uint32_t gx = gate ? (Q < 592u ? Q : 592u) : Q;   // gated: small grid-stride grid
     const size_t smem = (size_t)(G < lists ? G : lists) * k * sizeof(uint64_t);
     cudaError_t e = cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(kMergeSmemKeys * 2 * sizeof(uint64_t)));
@@ -155,7 +163,7 @@ cudaError_t launch_merge(const uint64_t* keys, uint32_t Q, uint32_t lists, uint3
     while (cur_lists > G) {
         const uint32_t nxt = (cur_lists + G - 1) / G;
         uint64_t* dst = flip ? bufB : bufA;
-        merge_lists_kernel<<<dim3(Q, nxt), 256, (size_t)G * k * 8, stream>>>(cur, cur_lists, q_stride, list_stride, k,
+        merge_lists_kernel<<<dim3(gx, nxt), 256, (size_t)G * k * 8, stream>>>(cur, Q, cur_lists, q_stride, list_stride, k,
                                                                              G, dst, nullptr, nullptr, gate);
         count_launch();
         e = cudaGetLastError();
@@ -167,7 +175,7 @@ cudaError_t launch_merge(const uint64_t* keys, uint32_t Q, uint32_t lists, uint3
         flip ^= 1;
     }
     // last pass: decoded ids/distances, or (out_keys) the merged key list itself
-    merge_lists_kernel<<<dim3(Q, 1), 256, smem, stream>>>(cur, cur_lists, q_stride, list_stride, k, G, out_keys,
+    merge_lists_kernel<<<dim3(gx, 1), 256, smem, stream>>>(cur, Q, cur_lists, q_stride, list_stride, k, G, out_keys,
                                                           out_keys ? nullptr : out_rows, out_keys ? nullptr : out_dists,
                                                           gate);
     count_launch();
