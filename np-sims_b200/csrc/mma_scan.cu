@@ -219,10 +219,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
     if (tid == 0) {
         for (uint32_t s = 0; s < PS; ++s) {
             mbar_init(&p_full[s], 1);
-            mbar_init(&p_empty[s], kMmaExpWarps);
+            mbar_init(&p_empty[s], kMmaExpWarps / 2);    // one expander set per stage
         }
         for (uint32_t s = 0; s < NG; ++s) {
-            mbar_init(&g_full[s], kMmaExpWarps);
+            mbar_init(&g_full[s], kMmaExpWarps / 2);     // one expander set per issuer
             mbar_init(&g_empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 else expand_row_kblock<4, 8>(tile_base, r, w, nvalid);
             }
         };
-        uint32_t ps = 0, pph = 0, t_idx = 0, lg2[2] = {0, 0};   // lg2[mw]: groups produced for issuer mw
+        static_assert(kMmaExpWarps == 8, "two expander sets of four warps");
+        uint32_t pph = 0, t_idx = 0, lg2[1] = {0};   // pph: parity of my packed stage; lg2[0]: groups produced by my set
         for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x) {
             const uint32_t chunk = item / p.num_qtiles, qt = item - chunk * p.num_qtiles;
             const uint32_t q0 = qt * NT;
@@ -404,38 +405,48 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(b_full);
+            // A tiles.  The expander warps work as TWO independent sets of kMmaExpWarps/2 warps, one per
+            // MMA issuer / accumulator buffer (set s takes the tiles with t_idx % 2 == s, whose packed
+            // rows always sit in stage s of the two-stage packed ring).  Expanding one tile is a latency
+            // chain (barrier wait, shared loads, ~300 ALU ops, stores, proxy fence, arrive) that eight
+            // warps together could not shorten; two tiles in flight hide half of it.
             for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
+                if ((t_idx & 1u) != part) continue;
                 const unsigned long long row0 = (unsigned long long)phase_tile(p, i) * kMmaTileRows;
                 const bool valid = row0 + u < p.N;
-                mbar_wait_relaxed(&p_full[ps], pph);
+                mbar_wait_relaxed(&p_full[part], pph);
                 if (u == 0 && part == 0) NPS_TRACE(1, 3);   // packed tile landed
-                const uint64_t* my = reinterpret_cast<const uint64_t*>(smem + L.p_off + ps * L.p_stride) + (size_t)u * W;
-                const uint32_t mw = t_idx & 1u;
-                uint32_t lg = mw ? lg2[1] : lg2[0];
+                const uint64_t* my = reinterpret_cast<const uint64_t*>(smem + L.p_off + part * L.p_stride) + (size_t)u * W;
+                uint32_t lg = lg2[0];
                 for (uint32_t g = 0; g < GPT; ++g, ++lg) {
-                    const uint32_t slot = mw * RG + (lg & (RG - 1u)), par = (lg >> (RG - 1u)) & 1u;
+                    const uint32_t slot = part * RG + (lg & (RG - 1u)), par = (lg >> (RG - 1u)) & 1u;
                     mbar_wait_relaxed(&g_empty[slot], par ^ 1u);
                     if (u == 0 && part == 0) NPS_TRACE(1, 1);   // group free
                     const uint32_t kb0 = g * GS, kb1 = min(kb0 + GS, KB);
                     for (uint32_t kb = kb0; kb < kb1; ++kb) {
-                        // this thread's two words of the K-block (4 kb + 2 part, + 1): ONE 16-byte load when
-                        // the row width is even (row strides of 64/128/256 bytes put every lane of a warp on
-                        // the same banks; four 8-byte loads per thread cost ~1000 cycles per K-block there)
+                        // this thread's four words of the K-block: 16-byte loads when the row width is even
+                        // (row strides of 64/128/256 bytes put every lane of a warp on the same banks; 8-byte
+                        // loads cost ~1000 cycles per K-block there)
                         const uint32_t nw = valid ? min(4u, W - 4u * kb) : 0u;
                         uint64_t w[4] = {0ull, 0ull, 0ull, 0ull};
-                        const uint32_t j0 = 2u * part;
                         if ((W & 1u) == 0u) {
-                            if (j0 < nw) {
-                                const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(my + 4 * kb + j0);
-                                w[j0] = t.x;
-                                w[j0 + 1] = t.y;
+                            if (nw > 0u) {
+                                const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(my + 4 * kb);
+                                w[0] = t.x;
+                                w[1] = t.y;
+                            }
+                            if (nw > 2u) {
+                                const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(my + 4 * kb + 2);
+                                w[2] = t.x;
+                                w[3] = t.y;
                             }
                         } else {
-                            if (j0 < nw) w[j0] = my[4 * kb + j0];
-                            if (j0 + 1 < nw) w[j0 + 1] = my[4 * kb + j0 + 1];
+#pragma unroll
+                            for (uint32_t j = 0; j < 4; ++j)
+                                if (j < nw) w[j] = my[4 * kb + j];
                         }
                         if (!(p.debug & 2u))
-                            expand(base + L.a_off + (slot * GS + (kb - kb0)) * kMmaAStageBytes, u, w, nw);
+                            expand_row_kblock<0, 8>(base + L.a_off + (slot * GS + (kb - kb0)) * kMmaAStageBytes, u, w, nw);
                     }
                     if (u == 0 && part == 0) NPS_TRACE(1, 4);   // group expanded (stores issued)
                     fence_proxy_async_smem();
@@ -444,13 +455,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                     if (lane == 0) mbar_arrive(&g_full[slot]);
                     if (u == 0 && part == 0) NPS_TRACE(1, 2);   // group written
                 }
-                if (mw) lg2[1] = lg; else lg2[0] = lg;
+                lg2[0] = lg;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&p_empty[ps]);
-                if (++ps == PS) {
-                    ps = 0;
-                    pph ^= 1u;
-                }
+                if (lane == 0) mbar_arrive(&p_empty[part]);
+                pph ^= 1u;
             }
         }
     } else {
