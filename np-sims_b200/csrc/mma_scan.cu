@@ -398,8 +398,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
             const uint32_t i1 = min(i0 + p.tiles_per_chunk, p.phase_tiles);
             // B (query tile) is resident for the whole item; the previous item's MMAs must have
             // retired before it is overwritten.
-            if (t_idx > 0) mbar_wait(&acc_full[(t_idx - 1) & 1u], ((t_idx - 1) >> 1) & 1u);
-            if (t_idx > 1) mbar_wait(&acc_full[(t_idx - 2) & 1u], ((t_idx - 2) >> 1) & 1u);
+            // Each expander set waits for ITS OWN buffer's last tile only — it has just expanded that tile,
+            // so the barrier cannot be more than one phase behind and the parity test is unambiguous (a set
+            // waiting on the other, possibly lagging, set's barrier can be two phases ahead of it and see
+            // the stale parity as "done": measured as wrong results on 4 % of the C2 queries) — and the two
+            // sets then meet on a named barrier.
+            if (t_idx > 0) {
+                const uint32_t last = ((t_idx - 1u) & 1u) == part ? t_idx - 1u : t_idx - 2u;   // my set's last tile
+                if (last < t_idx) mbar_wait(&acc_full[part], (last >> 1) & 1u);
+            }
+            named_bar_sync(2, kMmaExpWarps * 32);
             for (uint32_t n = u; n < NT; n += kMmaTileRows) {
                 const bool valid = q0 + n < p.Q;
                 const uint64_t* src = p.queries + (size_t)(valid ? q0 + n : 0) * W;

@@ -114,6 +114,27 @@ def test_mma_wide_signatures_equal_popc_scan(nps, force_mma, w, k):
     assert np.array_equal(r1[7].cpu().numpy().view(np.uint64), want_r)
 
 
+def test_mma_c2_shape_every_query_equals_popc_scan(nps, force_mma):
+    # BASELINE config C2 at full size (400k x 640 bits, 10k queries): many work items per CTA, item
+    # boundaries where the two expander sets of the kernel run apart.  A parity-aliased barrier wait
+    # there once corrupted the query tile of ~4 % of the queries, nondeterministically, while every
+    # smaller shape passed — so: the full shape, every query, several runs.
+    import torch
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    H = torch.randint(-2**63, 2**63 - 1, (400_000, 10), dtype=torch.int64, device="cuda", generator=g)
+    Q = torch.randint(-2**63, 2**63 - 1, (10_000, 10), dtype=torch.int64, device="cuda", generator=g)
+    Q[:2000] = H[torch.randint(0, 400_000, (2000,), device="cuda", generator=g)]
+    force_mma.set_scan_path(force_mma.SCAN_POPC)
+    want = nps.hamming_top_n(H, Q, 10)
+    force_mma.set_scan_path(force_mma.SCAN_MMA)
+    for _ in range(4):
+        got = nps.hamming_top_n(H, Q, 10)
+        assert force_mma.raw("nps_last_scan_path")() == force_mma.SCAN_MMA
+        bad = (got.view(torch.int64) != want.view(torch.int64)).any(dim=1)
+        assert int(bad.sum()) == 0, bad.nonzero()[:8].flatten().tolist()
+
+
 def test_mma_duplicates_and_index_ties(nps, force_mma):
     rng = np.random.default_rng(9)
     h = np.repeat(rand_sigs(rng, 40, 3), 300, axis=0)            # 12000 rows, each signature 300 times
