@@ -277,6 +277,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
     __syncthreads();
     tc_fence_after();
 
+    // Everything above touched only this CTA's shared and tensor memory; from here on the kernel reads
+    // what the previous launch in the stream (the select of the phase before) wrote.
+    pdl_wait();
+    pdl_launch_dependents();
     const uint32_t total_items = p.num_chunks * p.num_qtiles;
     const uint32_t row_bytes = W * 8;
     NPS_DEV(uint32_t trace_n = 0;)
@@ -657,13 +661,30 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
     if (warp == kWarpMma) tmem_dealloc(tmem_base, 512);
 }
 
-cudaError_t launch_mma_scan(const MmaScanParams& p, int grid, size_t smem, cudaStream_t stream) {
+// Launch with (pdl = true) or without the programmatic-stream-serialization attribute.
+template <typename Kern, typename Params>
+static cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                              const Params& p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+cudaError_t launch_mma_scan(const MmaScanParams& p, int grid, size_t smem, cudaStream_t stream, bool pdl) {
     auto kern = p.dense ? mma_scan_kernel<true> : mma_scan_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, kMmaThreads, smem, stream>>>(p);
+    e = launch_pdl(kern, dim3(grid), dim3(kMmaThreads), smem, stream, pdl, p);
     count_launch();
-    return cudaGetLastError();
+    return e;
 }
 
 // =============================================================================================
@@ -676,6 +697,8 @@ constexpr int kSelectThreads = 128;
 
 __global__ void __launch_bounds__(kSelectThreads) mma_select_kernel(const MmaSelectParams p) {
     extern __shared__ __align__(16) uint64_t skeys[];
+    pdl_wait();
+    pdl_launch_dependents();
     const uint32_t q = blockIdx.x;
     const int tid = threadIdx.x;
     if (q >= p.Q) {   // padding entries of the threshold arrays: never pass
@@ -740,6 +763,8 @@ constexpr int kSelectWarps = 8;
 
 __global__ void __launch_bounds__(kSelectWarps * 32) mma_select_warp_kernel(const MmaSelectParams p) {
     extern __shared__ __align__(16) uint64_t skeys[];
+    pdl_wait();
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * kSelectWarps + warp;
     if (q >= p.Qpad) return;
@@ -805,22 +830,23 @@ __global__ void __launch_bounds__(kSelectWarps * 32) mma_select_warp_kernel(cons
     }
 }
 
-cudaError_t launch_mma_select(const MmaSelectParams& p, cudaStream_t stream) {
+cudaError_t launch_mma_select(const MmaSelectParams& p, cudaStream_t stream, bool pdl) {
     if (p.k <= 32 && (size_t)(p.k + p.cap) * 8 * kSelectWarps <= 160 * 1024) {
         const size_t smem = (size_t)(p.k + p.cap) * 8 * kSelectWarps;
         cudaError_t e =
             cudaFuncSetAttribute(mma_select_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        mma_select_warp_kernel<<<(p.Qpad + kSelectWarps - 1) / kSelectWarps, kSelectWarps * 32, smem, stream>>>(p);
+        e = launch_pdl(mma_select_warp_kernel, dim3((p.Qpad + kSelectWarps - 1) / kSelectWarps), dim3(kSelectWarps * 32),
+                       smem, stream, pdl, p);
         count_launch();
-        return cudaGetLastError();
+        return e;
     }
     const size_t smem = (size_t)p.sort_cap * 8;
     cudaError_t e = cudaFuncSetAttribute(mma_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    mma_select_kernel<<<p.Qpad, kSelectThreads, smem, stream>>>(p);
+    e = launch_pdl(mma_select_kernel, dim3(p.Qpad), dim3(kSelectThreads), smem, stream, pdl, p);
     count_launch();
-    return cudaGetLastError();
+    return e;
 }
 
 
@@ -981,6 +1007,9 @@ cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned 
     // flag + counters are contiguous at the start of the workspace
     cudaError_t e = cudaMemsetAsync(w8, 0, pl.off_thrT, stream);
     if (e != cudaSuccess) return e;
+    // Programmatic dependent launch between the back-to-back scan / select launches, unless per-phase
+    // events are being recorded between them (profiling) or NPS_NO_PDL is set (development).
+    const bool use_pdl = phase_events == nullptr && getenv("NPS_NO_PDL") == nullptr;
     for (uint32_t ph = 0; ph < pl.num_phases; ++ph) {
         const MmaPhase& P = pl.phase[ph];
         const bool last = ph + 1 == pl.num_phases;
@@ -1025,7 +1054,9 @@ cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned 
                 e = cudaEventRecord(phase_events[2 * ph], stream);
                 if (e != cudaSuccess) return e;
             }
-            e = launch_mma_scan(sp, (int)P.grid, pl.smem, stream);
+            // the scan of phase >= 1 directly follows the select of the phase before: let its prologue
+            // overlap that kernel's tail (not when events or trace copies sit between the launches)
+            e = launch_mma_scan(sp, (int)P.grid, pl.smem, stream, use_pdl && ph > 0 && !sp.trace);
             if (e != cudaSuccess) return e;
             if (phase_events) {
                 e = cudaEventRecord(phase_events[2 * ph + 1], stream);
@@ -1060,7 +1091,7 @@ cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned 
         se.fixed_cnt = ph == 0 ? (int)(P.tiles * kMmaTileRows) : -1;
         se.first = ph == 0;
         se.sort_cap = pl.sort_cap;
-        e = launch_mma_select(se, stream);
+        e = launch_mma_select(se, stream, use_pdl && P.tiles != 0);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;

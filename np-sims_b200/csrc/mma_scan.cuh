@@ -122,8 +122,8 @@ struct MmaSelectParams {
     uint32_t sort_cap;       // shared-memory sort capacity (power of two >= k + cap)
 };
 
-cudaError_t launch_mma_scan(const MmaScanParams& p, int grid, size_t smem, cudaStream_t stream);
-cudaError_t launch_mma_select(const MmaSelectParams& p, cudaStream_t stream);
+cudaError_t launch_mma_scan(const MmaScanParams& p, int grid, size_t smem, cudaStream_t stream, bool pdl = false);
+cudaError_t launch_mma_select(const MmaSelectParams& p, cudaStream_t stream, bool pdl = false);
 
 // ---- host-side plan: tile shape, candidate capacity, phase schedule -------------------------
 constexpr int kMmaMaxPhases = 24;

@@ -150,6 +150,13 @@ __device__ __forceinline__ void tmem_ld8_at(uint32_t taddr, uint32_t (&v)[LEN]) 
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Programmatic dependent launch: a kernel launched with programmaticStreamSerializationAllowed may
+// start (prologue: barrier init, TMEM allocation) while its predecessor in the stream is still
+// draining; pdl_wait() blocks until the predecessor grid has completed and its writes are visible
+// (a no-op without the launch attribute).  pdl_launch_dependents() lets the successor start early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
