@@ -505,3 +505,22 @@ def test_recall_harness_index_files_use_the_reference_format(nps, tmp_path, monk
     one, _ = rec.run_algorithm("lsh_pure_c", q[:3], h2, p2, None)
     full = oracle.hamming(h2, oracle.index_np(q[:1], p2)[0])
     assert oracle.tie_aware_equal(full, one[0], ids[0], 10)
+
+
+def test_query_stream_pipeline_equals_query_batch(nps, c1_glove):
+    """np_sims.pipeline.QueryStream: batches streamed with copies overlapped == lsh.query_batch per batch."""
+    import np_sims.lsh as lsh
+    from np_sims.pipeline import QueryStream
+    X, H = c1_glove["X"], c1_glove["H"]
+    np.random.seed(0)
+    W = lsh.create_projections(640, 300)
+    batches = [X[i * 100:(i + 1) * 100 + (7 if i == 3 else 0)] for i in range(6)]      # one ragged batch
+    qs = QueryStream(H, W, n=10, depth=2)
+    got = [ids.copy() for ids in qs.map(batches)]
+    assert len(got) == len(batches)
+    for b, ids in zip(batches, got):
+        assert np.array_equal(ids, lsh.query_batch(b, H, W, n=10))
+    t0 = qs.submit(batches[0])
+    assert np.array_equal(qs.result(t0), got[0])
+    with pytest.raises(ValueError):
+        qs.result(t0 - 5)
