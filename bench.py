@@ -2,24 +2,35 @@
 """bench.py — hamming_top_n queries/s on B200 (BASELINE.json metric), one JSON line.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c4]
+                    [--shard auto|rows|queries]
 
 Workload (default, BASELINE config C2): GloVe-6B-shaped synthetic 400k x 300 fp32 vectors,
 640-bit signatures (10 x uint64), 10 000 query vectors, top-10.  One STEP = one pass of the hot
-path over the whole query batch: hash the 10k query vectors (K1), fused Hamming scan + top-10
-over the signature table (K2), block merge (K3) [+ NCCL all-gather of candidate keys and
-shard merge (K4) when N > 1].  The signature table is built once by K1 before timing and stays
-resident in HBM; with N GPUs it is row-sharded N ways (strong scaling: total work fixed).
+path over the whole query batch: hash the 10k query vectors (K1T, tcgen05 TF32-split GEMM),
+batched Hamming scan + top-10 over the signature table (K2T: tcgen05 kind::mxf4 phases + select
+kernels; a gated XOR+POPC repair pass that is a no-op unless a candidate buffer overflowed)
+[+ one NCCL all-gather when N > 1].  The signature table is built once by K1T before timing and
+stays resident in HBM.  With N GPUs (strong scaling: total work fixed) the 32 MB table is
+replicated and the query batch split N ways (`--shard queries`, the automatic choice for tables
+<= 4 GiB); `--shard rows` splits the table by rows instead (all-gather of candidate keys + K4
+merge), which is what the 12.8 GB C4 workload uses.
 
-`value`  : queries/s with the query vectors already in HBM (device-timed, CUDA events).
+`value`  : queries/s with the query vectors already in HBM (device-timed, CUDA events, L2
+           evicted between iterations).
 `e2e`    : the same step through the public API with HOST (pinned) query vectors in and HOST
-           ids out, copies inside the timed region.
-`roofline`: the dominant kernel (scan_topk_kernel) timed per launch with CUDA events on the
-           launching stream (nps_profile_*), against MEASURED_PEAKS.json.
+           ids out, copies inside the timed region, one blocking call per step;
+           `e2e.pipelined`: the same batches streamed through np_sims.pipeline.QueryStream
+           (two batches in flight, copies overlapped with the search).
+`roofline`: the dominant launch (mma_scan_kernel, last phase) timed with CUDA events recorded by
+           the library on the launching stream (nps_profile_*), against 4 x the measured bf16
+           peak of MEASURED_PEAKS.json (kind::mxf4 : bf16 = 4 : 1); `roofline_stream`: the
+           HBM-bound single-query scan (scan_topk_kernel) against the measured HBM peak.
 `cpu_baseline` / --impl reference: the reference's own ufunc (oracle/_ref, compiled from the
            unmodified np_sims/ufunc.c) driven exactly like benchmark/glove.py:183-199 — a
            ThreadPoolExecutor over all host cores, one query per task.
 
-bench.py is one of the three places allowed to touch oracle/ — only for the CPU legs.
+bench.py is one of the three places allowed to touch oracle/ — only for the CPU legs and for the
+parity spot-check of the timed step.
 """
 from __future__ import annotations
 

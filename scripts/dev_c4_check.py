@@ -31,7 +31,7 @@ phases = _lib.profile_last_phases(); _lib.raw("nps_profile_enable")(0)
 flop = 2.0 * n * q * w * 64
 print(f"n={n} w={w} q={q} k={k}: {ms:.1f} ms -> {q/ms*1e3:.0f} q/s, {flop/ms/1e9:.0f} TFLOP/s; plan={_lib.last_mma_plan()}")
 print("phases (tiles, ms):", [(t, round(m, 2)) for t, m in phases])
-sample = torch.cat([torch.arange(0, 32, device="cuda"), torch.arange(q - 31, q, device="cuda")])
+sample = torch.cat([torch.arange(0, 32, device="cuda"), torch.arange(q - 31, q, device="cuda"), torch.randint(0, q, (min(q, 2000),), device="cuda", generator=g)])
 _lib.set_scan_path(_lib.SCAN_POPC)
 r0, d0 = np_sims.hamming_top_n(H, Q[sample].contiguous(), k, return_distances=True)
 torch.cuda.synchronize()
