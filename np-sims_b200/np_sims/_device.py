@@ -11,10 +11,18 @@ def torch():
     return _torch
 
 
+_cuda_ok = False
+
+
 def require_cuda():
+    """torch, after checking once that a CUDA device exists (torch.cuda.is_available() costs ~3 us
+    per call and the single-query entry points used to make nine of them)."""
+    global _cuda_ok
     t = torch()
-    if not t.cuda.is_available():
-        raise RuntimeError("npsims_b200: no CUDA device available (there is no CPU fallback)")
+    if not _cuda_ok:
+        if not t.cuda.is_available():
+            raise RuntimeError("npsims_b200: no CUDA device available (there is no CPU fallback)")
+        _cuda_ok = True
     return t
 
 
