@@ -524,3 +524,24 @@ def test_query_stream_pipeline_equals_query_batch(nps, c1_glove):
     assert np.array_equal(qs.result(t0), got[0])
     with pytest.raises(ValueError):
         qs.result(t0 - 5)
+
+
+def test_single_query_api_from_a_thread_pool(nps, c1_glove):
+    """The reference drives its single-query API from a ThreadPoolExecutor (benchmark/glove.py:183-199,
+    GIL released in the ufunc).  The drop-in must give the same answers when called that way."""
+    from concurrent.futures import ThreadPoolExecutor
+    import np_sims.lsh as lsh
+    X, H = c1_glove["X"], c1_glove["H"]
+    np.random.seed(0)
+    W = lsh.create_projections(640, 300)
+    Hd = lsh.index(X, W)                                   # DeviceArray: table stays resident
+    assert np.array_equal(np.asarray(Hd), H)
+    want = [np.asarray(lsh.query(X[i], Hd, W)[0]) for i in range(64)]
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        got = list(ex.map(lambda i: np.asarray(lsh.query(X[i], Hd, W)[0]), range(64)))
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        got = list(ex.map(lambda i: nps.hamming_top_n(Hd, H[i], 10), range(64)))
+    for i, b in enumerate(got):
+        assert np.array_equal(b, oracle.top_k_canonical(H, H[i], 10)[0])
