@@ -457,6 +457,24 @@ def run_b200(args, wl):
             _, _, cpu = cpu_reference_run(wl, args.cpu_sample, steps=64, warmup=1, H=H_host, W=Wn, qvecs=qvecs_all,
                                           time_budget_s=20.0)
         # summed over ranks: row sharding uploads the whole batch on every rank, query sharding one slice each
+        # hashing parity of the timed step's K1T (north-star: "flipped-bit rate reported"): bare tensor-core
+        # signs and final signatures of the query batch against the float64 kernel
+        hash_report = None
+        if W is not None:
+            def bits_differing(a, b):
+                x = (a ^ b).cpu().numpy().view(np.uint64)
+                return int(np.unpackbits(x.view(np.uint8)).sum())
+            s_exact = lsh.hash_vectors(qvecs_dev, W, exact_only=True)
+            s_final = lsh.hash_vectors(qvecs_dev, W)
+            st = lsh.hash_stats()
+            s_raw = lsh.hash_vectors(qvecs_dev, W, tf32_raw=True)
+            nbits = int(qvecs_dev.shape[0]) * wl["bits"]
+            hash_report = {"path": st["path"], "bits": nbits,
+                           "tolerance": f"(8 + dims/4) * 2^-22 * |x| * max|w| = {(8 + wl['dims'] / 4) * 2.0 ** -22:.3e} |x|",
+                           "recomputed_in_float64": st.get("recomputed"), "recomputed_frac": (st.get("recomputed") or 0) / nbits,
+                           "flipped_bits_before_fixup": bits_differing(s_raw, s_exact),
+                           "flipped_bits_final": bits_differing(s_final, s_exact)}
+            assert hash_report["flipped_bits_final"] == 0, "K1T signatures differ from the float64 kernel"
         h2d = (qvecs_all.nbytes if W is not None else nq * words * 8) * (1 if by_query else world)
         line = {
             "metric": "hamming_top_n queries/s", "value": value, "unit": "queries/s", "n_gpus": world,
@@ -479,6 +497,7 @@ def run_b200(args, wl):
             "gpu_launches": int(launches),
             "roofline": roofline,
             "roofline_stream": stream,
+            "hash": hash_report,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
