@@ -470,7 +470,8 @@ def run_b200(args, wl):
             s_raw = lsh.hash_vectors(qvecs_dev, W, tf32_raw=True)
             nbits = int(qvecs_dev.shape[0]) * wl["bits"]
             hash_report = {"path": st["path"], "bits": nbits,
-                           "tolerance": f"(8 + dims/4) * 2^-22 * |x| * max|w| = {(8 + wl['dims'] / 4) * 2.0 ** -22:.3e} |x|",
+                           "encoding": "bf16 x 2 (kind::f16), three products, separate correction accumulator",
+                           "tolerance": f"(52 + dims/4) * 2^-22 * |x| * max|w| = {(52 + wl['dims'] / 4) * 2.0 ** -22:.3e} |x|",
                            "recomputed_in_float64": st.get("recomputed"), "recomputed_frac": (st.get("recomputed") or 0) / nbits,
                            "flipped_bits_before_fixup": bits_differing(s_raw, s_exact),
                            "flipped_bits_final": bits_differing(s_final, s_exact)}

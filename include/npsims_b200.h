@@ -190,12 +190,21 @@ int nps_rerank_top_n(const uint64_t *d_hashes, uint64_t num_hashes, uint32_t wor
  * projection) pairs below that (0.03 % at dims = 300) and all rows with a zero / tiny / huge /
  * non-finite norm are recomputed in float64 by a fix-up kernel, so the signatures equal those of
  * nps_project_sign_pack_f64.  Needs dims % 4 == 0 and 16-byte aligned inputs.
- * d_projections_split: float [2, num_projections, dims] from nps_project_split_projections (do it
+ * d_projections_split: nps_project_split_bytes() bytes filled by nps_project_split_projections (do it
  * once per projection matrix); d_projections_f64: the float64 matrix (fix-up);
  * projection_norm_max = max_j |projections[j]| (1.0 for lsh.create_projections).
  * If the fix-up list overflows (degenerate input) the call is redone in float64 by a gated launch
  * on the device — no host round trip.  nps_project_sign_pack_stats (diagnostic; synchronises the
  * stream) returns how many pairs went to the fix-up list and its capacity. */
+/* size in bytes of the split buffer for nps_project_split_projections / nps_project_sign_pack (both
+ * operand encodings: float32 [2, B, dims] TF32 parts, then bfloat16 [2, B, dims rounded up to 8]) */
+size_t nps_project_split_bytes(uint32_t num_projections, uint32_t dims);
+/* which operand encoding nps_project_sign_pack uses: BF16 x 2 on kind::f16 (AUTO, the default; tolerance
+ * (52 + dims/4) * 2^-22) or TF32 x 2 on kind::tf32 (tolerance (8 + dims/4) * 2^-22) */
+#define NPS_HASH_AUTO 0
+#define NPS_HASH_TF32 1
+#define NPS_HASH_BF16 2
+int nps_set_hash_path(int path);
 int nps_project_split_projections(const double *d_projections_f64, uint32_t num_projections, uint32_t dims,
                                   float *d_out_split, void *stream);
 size_t nps_project_sign_pack_workspace_bytes(uint64_t num_vectors, uint32_t num_projections);

@@ -556,6 +556,15 @@ size_t nps_project_sign_pack_workspace_bytes(uint64_t num_vectors, uint32_t num_
     return project_tc_workspace_bytes(num_vectors, num_projections, nullptr);
 }
 
+size_t nps_project_split_bytes(uint32_t num_projections, uint32_t dims) { return project_split_bytes(num_projections, dims); }
+
+static int g_hash_path = NPS_HASH_AUTO;
+int nps_set_hash_path(int path) {
+    if (path != NPS_HASH_AUTO && path != NPS_HASH_TF32 && path != NPS_HASH_BF16) return fail(NPS_EINVAL, "bad hash path %d", path);
+    g_hash_path = path;
+    return NPS_OK;
+}
+
 int nps_project_split_projections(const double* d_projections_f64, uint32_t num_projections, uint32_t dims,
                                   float* d_out_split, void* stream) {
     if (!d_projections_f64 || !d_out_split) return fail(NPS_EINVAL, "null pointer");
@@ -584,7 +593,7 @@ int nps_project_sign_pack(const float* d_vectors, uint64_t num_vectors, uint32_t
     if (rc) return rc;
     NPS_CUDA(launch_project_tc(d_vectors, num_vectors, dims, d_projections_f32, d_projections_f64, num_projections,
                                projection_norm_max, d_out, d_workspace, dev.sm_count, dev.smem_optin,
-                               (cudaStream_t)stream));
+                               (cudaStream_t)stream, g_hash_path != NPS_HASH_TF32));
     return NPS_OK;
 }
 

@@ -86,6 +86,79 @@ __device__ __forceinline__ uint32_t tf32_low_part(uint32_t x) {
     return rn_tf32(__uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u));
 }
 
+// Epilogue shared by both operand encodings: signs of C1 + C2 -> uint64 words, uncertain entries ->
+// fix-up list (one atomic per warp and item).  Accumulator buffer b holds C1 at columns [2 NT b, +NT)
+// and C2 right behind it.
+template <uint32_t NT>
+__device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t tmem_base, uint64_t* acc_full,
+                                                 uint64_t* acc_empty, int warp, int lane, unsigned long long total) {
+        const uint32_t quarter = warp & 3u;
+        const uint32_t r_in_tile = quarter * 32u + lane;
+        const uint32_t words_per_row = p.B / 64u;
+        constexpr uint32_t G = NT / 32u;       // 32-column groups per item
+        uint32_t t_idx = 0;
+        for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx) {
+            const unsigned long long mt = item / p.num_ntiles;
+            const uint32_t nt = (uint32_t)(item - mt * p.num_ntiles);
+            const uint32_t buf = t_idx & 1u;
+            const unsigned long long row = mt * kPtTileRows + r_in_tile;
+            const bool valid = row < p.N;
+            const float norm = valid ? __ldg(p.norms + row) : 1.f;
+            const bool tame = norm >= 1e-18f && norm <= 1e18f;     // false for 0, tiny, huge, inf, NaN
+            const float tol = p.tol_scale * norm;
+            mbar_wait(&acc_full[buf], (t_idx >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * (2u * NT);
+            uint32_t sign_m[G], unsure_m[G];
+#pragma unroll
+            for (uint32_t g = 0; g < G; ++g) {
+                uint32_t v1[32], v2[32];
+                tmem_ld32(t_addr + g * 32u, v1);
+                tmem_ld32(t_addr + NT + g * 32u, v2);
+                tmem_ld_wait();
+                uint32_t bits = 0, unsure = 0;      // per column: sign, |acc| below the tolerance
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float a = __uint_as_float(v1[j]) + __uint_as_float(v2[j]);
+                    bits |= (a >= 0.f ? 1u : 0u) << j;
+                    unsure |= (fabsf(a) < tol ? 1u : 0u) << j;
+                }
+                sign_m[g] = bits;
+                unsure_m[g] = !valid ? 0u : (tame ? unsure : 0xFFFFFFFFu);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);   // accumulator free before the global traffic below
+            if (valid) {
+#pragma unroll
+                for (uint32_t g = 0; g < G; g += 2)
+                    p.out[row * words_per_row + (nt * NT + g * 32u) / 64u] =
+                        (uint64_t)sign_m[g] | ((uint64_t)sign_m[g + 1] << 32);
+            }
+            uint32_t mine = 0;
+#pragma unroll
+            for (uint32_t g = 0; g < G; ++g) mine += __popc(unsure_m[g]);
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const uint32_t all = __shfl_sync(0xffffffffu, incl, 31);
+            if (all) {   // warp-uniform
+                uint32_t basepos = 0;
+                if (lane == 31) basepos = atomicAdd(p.fix_count, all);
+                basepos = __shfl_sync(0xffffffffu, basepos, 31);
+                uint32_t pos = basepos + incl - mine;
+#pragma unroll
+                for (uint32_t g = 0; g < G; ++g)
+                    for (uint32_t m = unsure_m[g]; m; m &= m - 1u, ++pos)
+                        if (pos < p.fix_cap)
+                            p.fix[pos] = (row << 16) | (unsigned long long)(nt * NT + g * 32u + (__ffs(m) - 1));
+            }
+        }
+}
+
 // Stage layout: [xh tile 16 KB][xl tile 16 KB][wh tile NT x 128 B][wl tile NT x 128 B]
 template <uint32_t NT>
 __global__ void __launch_bounds__(kPtThreads, 1)
@@ -214,94 +287,210 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             }
         }
     } else {
-        // ===== epilogue: signs -> uint64 words, uncertain entries -> fix-up list (one atomic per warp and item)
-        const uint32_t quarter = warp & 3u;
-        const uint32_t r_in_tile = quarter * 32u + lane;
-        const uint32_t words_per_row = p.B / 64u;
-        constexpr uint32_t G = NT / 32u;       // 32-column groups per item
-        uint32_t t_idx = 0;
-        for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx) {
-            const unsigned long long mt = item / p.num_ntiles;
-            const uint32_t nt = (uint32_t)(item - mt * p.num_ntiles);
-            const uint32_t buf = t_idx & 1u;
-            const unsigned long long row = mt * kPtTileRows + r_in_tile;
-            const bool valid = row < p.N;
-            const float norm = valid ? __ldg(p.norms + row) : 1.f;
-            const bool tame = norm >= 1e-18f && norm <= 1e18f;     // false for 0, tiny, huge, inf, NaN
-            const float tol = p.tol_scale * norm;
-            mbar_wait(&acc_full[buf], (t_idx >> 1) & 1u);
-            tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * (2u * NT);
-            uint32_t sign_m[G], unsure_m[G];
-#pragma unroll
-            for (uint32_t g = 0; g < G; ++g) {
-                uint32_t v1[32], v2[32];
-                tmem_ld32(t_addr + g * 32u, v1);
-                tmem_ld32(t_addr + NT + g * 32u, v2);
-                tmem_ld_wait();
-                uint32_t bits = 0, unsure = 0;      // per column: sign, |acc| below the tolerance
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float a = __uint_as_float(v1[j]) + __uint_as_float(v2[j]);
-                    bits |= (a >= 0.f ? 1u : 0u) << j;
-                    unsure |= (fabsf(a) < tol ? 1u : 0u) << j;
-                }
-                sign_m[g] = bits;
-                unsure_m[g] = !valid ? 0u : (tame ? unsure : 0xFFFFFFFFu);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);   // accumulator free before the global traffic below
-            if (valid) {
-#pragma unroll
-                for (uint32_t g = 0; g < G; g += 2)
-                    p.out[row * words_per_row + (nt * NT + g * 32u) / 64u] =
-                        (uint64_t)sign_m[g] | ((uint64_t)sign_m[g + 1] << 32);
-            }
-            uint32_t mine = 0;
-#pragma unroll
-            for (uint32_t g = 0; g < G; ++g) mine += __popc(unsure_m[g]);
-            uint32_t incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += up;
-            }
-            const uint32_t all = __shfl_sync(0xffffffffu, incl, 31);
-            if (all) {   // warp-uniform
-                uint32_t basepos = 0;
-                if (lane == 31) basepos = atomicAdd(p.fix_count, all);
-                basepos = __shfl_sync(0xffffffffu, basepos, 31);
-                uint32_t pos = basepos + incl - mine;
-#pragma unroll
-                for (uint32_t g = 0; g < G; ++g)
-                    for (uint32_t m = unsure_m[g]; m; m &= m - 1u, ++pos)
-                        if (pos < p.fix_cap)
-                            p.fix[pos] = (row << 16) | (unsigned long long)(nt * NT + g * 32u + (__ffs(m) - 1));
-            }
-        }
+        project_epilogue<NT>(p, tmem_base, acc_full, acc_empty, warp, lane, total);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// W (float64) -> [2, B, D] float32: wh = rn_tf32(w), wl = rn_tf32(w - wh); w - wh - wl <= 2^-22 |w|
-__global__ void __launch_bounds__(256) split_projections_kernel(const double* __restrict__ W, size_t n,
-                                                                float* __restrict__ out) {
-    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const double w = W[i];
-    const uint32_t hi = rn_tf32((float)w);
-    const uint32_t lo = rn_tf32((float)(w - (double)__uint_as_float(hi)));
-    out[i] = __uint_as_float(hi);
-    out[n + i] = __uint_as_float(lo);
+// =============================================================================================
+// BF16 x 2 variant (the default): the same three-product scheme with both operands split into two
+// BF16 terms, x = x0 + x1 (+ <= 2^-18 |x|), w = w0 + w1, on kind::f16 — twice the MMA rate of
+// kind::tf32 and half the operand bytes per flop, which is what bounds the TF32 kernel (shared-
+// memory bandwidth).  X still arrives as float32 by TMA (two 32-float boxes per 64-float K-block);
+// the splitter warps (thread = row) convert it into the two K-major SWIZZLE_128B BF16 tiles.
+// Accumulation model measured for kind::f16 too (scripts/ubench/umma_bf16_numerics.cu: 2 guard
+// bits, RZ write-back): per instruction (K = 16) (17/4 + 1) * 2^-23.  Budget relative to |x||w|:
+//      representation  x1.w1 + ex.w + x.ew        3 * 2^-18               =  48 * 2^-22
+//      C1 accumulation D/16 instructions x 5.25 * 2^-23                   =  0.164 * D * 2^-22
+// -> trusted when |C1 + C2| >= (52 + D/4) * 2^-22 * |x_i| max_j |w_j|.
+// Stage layout: [raw fp32 2 x 16 KB][x0 16 KB][x1 16 KB][w0 NT x 128 B][w1 NT x 128 B]
+// =============================================================================================
+constexpr int kPbKBlock = 64;
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {   // lo -> bits [0,16), hi -> bits [16,32)
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// two floats -> (x0 pair, x1 pair): x0 = bf16_rn(x), x1 = bf16_rn(x - x0)
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& h, uint32_t& l) {
+    h = pack_bf16x2(a, b);
+    l = pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xFFFF0000u));
+}
+
+template <uint32_t NT>
+__global__ void __launch_bounds__(kPtThreads, 1)
+project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                    const ProjTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const uint32_t S = p.stages;
+    constexpr uint32_t kWTile = NT * 128u;                      // NT projections x 64 bf16
+    constexpr uint32_t kRaw = 2u * kPtAStage, kOp = kPtAStage;  // 32 KB raw, 16 KB per bf16 X tile
+    constexpr uint32_t stage_bytes = kRaw + 2u * kOp + 2u * kWTile;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* split_done = full + S;
+    uint64_t* empty = split_done + S;
+    uint64_t* acc_full = empty + S;     // [2]
+    uint64_t* acc_empty = acc_full + 2; // [2]
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (uint32_t s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&split_done[s], 4);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_s);
+
+    const uint32_t KB = (p.D + kPbKBlock - 1) / kPbKBlock;
+    const unsigned long long total = p.num_mtiles * p.num_ntiles;
+
+    if (warp == 0) {
+        // ===== TMA producer
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x) {
+                const unsigned long long mt = item / p.num_ntiles;
+                const uint32_t nt = (uint32_t)(item - mt * p.num_ntiles);
+                for (uint32_t kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    const uint32_t dst = base + s * stage_bytes;
+                    mbar_arrive_expect_tx(&full[s], kRaw + 2u * kWTile);
+                    tma_load_2d(dst, &tm_x, kb * kPbKBlock, (uint32_t)(mt * kPtTileRows), &full[s]);
+                    tma_load_2d(dst + kPtAStage, &tm_x, kb * kPbKBlock + 32u, (uint32_t)(mt * kPtTileRows), &full[s]);
+                    tma_load_2d(dst + kRaw + 2u * kOp, &tm_w, kb * kPbKBlock, nt * NT, &full[s]);
+                    tma_load_2d(dst + kRaw + 2u * kOp + kWTile, &tm_w, kb * kPbKBlock, p.B + nt * NT, &full[s]);
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: [C1 | C2] += x0.[w0; w1] (one instruction of width 2 NT) ; C2 += x1.w0
+        const uint32_t idesc = umma_idesc(1, 1, kPtTileRows, NT);        // BF16 x BF16 -> F32
+        const uint32_t idesc2 = umma_idesc(1, 1, kPtTileRows, 2u * NT);
+        uint32_t s = 0, ph = 0, t_idx = 0;
+        for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx) {
+            const uint32_t buf = t_idx & 1u;
+            mbar_wait(&acc_empty[buf], ((t_idx >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t c1 = tmem_base + buf * (2u * NT), c2 = c1 + NT;
+            for (uint32_t kb = 0; kb < KB; ++kb) {
+                mbar_wait(&full[s], ph);
+                mbar_wait(&split_done[s], ph);
+                tc_fence_after();
+                if (pt_elect_one()) {
+                    const uint32_t st = base + s * stage_bytes;
+                    const uint64_t x0 = umma_desc_k_sw128(st + kRaw), x1 = umma_desc_k_sw128(st + kRaw + kOp);
+                    const uint64_t w0 = umma_desc_k_sw128(st + kRaw + 2u * kOp);   // w1 follows at + kWTile
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) {   // K = 16 bf16 (32 bytes) per instruction
+                        umma_f16(c1, x0 + 2u * j, w0 + 2u * j, idesc2, (kb | j) != 0u);
+                        umma_f16(c2, x1 + 2u * j, w0 + 2u * j, idesc, true);
+                    }
+                    umma_commit(&empty[s]);
+                    if (kb + 1 == KB) umma_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= 6) {
+        // ===== splitters: thread = row.  Output chunk j (8 bf16 = floats 8j .. 8j+7 of the K-block) comes from
+        // 16-byte chunks 2(j&3), 2(j&3)+1 of raw box j>>2; every access is the row's 128-byte line with the
+        // chunk index XORed by (row & 7): conflict-free for the eight rows of a quarter warp.
+        const uint32_t r = (uint32_t)tid - 192u, r7 = r & 7u;
+        const uint32_t rowoff = (r >> 3) * 1024u + r7 * 128u;
+        uint32_t s = 0, ph = 0;
+        for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x) {
+            for (uint32_t kb = 0; kb < KB; ++kb) {
+                mbar_wait(&full[s], ph);
+                uint8_t* st = smem + s * stage_bytes;
+#pragma unroll
+                for (uint32_t j = 0; j < 8; ++j) {
+                    const uint8_t* box = st + (j >> 2) * kPtAStage + rowoff;
+                    const uint32_t c0 = 2u * (j & 3u);
+                    const float4 a = *reinterpret_cast<const float4*>(box + ((c0 ^ r7) << 4));
+                    const float4 b = *reinterpret_cast<const float4*>(box + (((c0 + 1u) ^ r7) << 4));
+                    uint4 h, l;
+                    split_bf16x2(a.x, a.y, h.x, l.x);
+                    split_bf16x2(a.z, a.w, h.y, l.y);
+                    split_bf16x2(b.x, b.y, h.z, l.z);
+                    split_bf16x2(b.z, b.w, h.w, l.w);
+                    *reinterpret_cast<uint4*>(st + kRaw + rowoff + ((j ^ r7) << 4)) = h;
+                    *reinterpret_cast<uint4*>(st + kRaw + kOp + rowoff + ((j ^ r7) << 4)) = l;
+                }
+                fence_proxy_async_smem();   // generic-proxy stores -> visible to tcgen05.mma (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&split_done[s]);
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else {
+        project_epilogue<NT>(p, tmem_base, acc_full, acc_empty, warp, lane, total);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// W (float64) -> both operand encodings, back to back in one buffer (project_split_bytes):
+//   [2, B, D]  float32  wh = rn_tf32(w), wl = rn_tf32(w - wh)          w - wh - wl <= 2^-22 |w|
+//   [2, B, Dp] bfloat16 w0 = rn_bf16(w), w1 = rn_bf16(w - w0), Dp = D rounded up to 8 (16-byte rows for
+//              the tensor map), zero padded                             w - w0 - w1 <= 2^-18 |w|
+static size_t split_tf32_bytes(uint32_t B, uint32_t D) { return ((size_t)2 * B * D * 4 + 255) / 256 * 256; }
+static uint32_t split_dp(uint32_t D) { return (D + 7u) & ~7u; }
+size_t project_split_bytes(uint32_t B, uint32_t D) { return split_tf32_bytes(B, D) + (size_t)2 * B * split_dp(D) * 2; }
+
+__global__ void __launch_bounds__(256) split_projections_kernel(const double* __restrict__ W, uint32_t B, uint32_t D,
+                                                                uint32_t Dp, float* __restrict__ out,
+                                                                uint16_t* __restrict__ out16) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;    // over [B, Dp]
+    if (i >= (size_t)B * Dp) return;
+    const uint32_t row = (uint32_t)(i / Dp), col = (uint32_t)(i - (size_t)row * Dp);
+    const double w = col < D ? W[(size_t)row * D + col] : 0.0;
+    if (col < D) {
+        const uint32_t hi = rn_tf32((float)w);
+        const uint32_t lo = rn_tf32((float)(w - (double)__uint_as_float(hi)));
+        out[(size_t)row * D + col] = __uint_as_float(hi);
+        out[(size_t)B * D + (size_t)row * D + col] = __uint_as_float(lo);
+    }
+    const uint32_t b0 = pack_bf16x2((float)w, 0.f) & 0xFFFFu;
+    const uint32_t b1 = pack_bf16x2((float)(w - (double)__uint_as_float(b0 << 16)), 0.f) & 0xFFFFu;
+    out16[i] = (uint16_t)b0;
+    out16[(size_t)B * Dp + i] = (uint16_t)b1;
 }
 
 cudaError_t launch_split_projections(const double* W64, uint32_t B, uint32_t D, float* out, cudaStream_t stream) {
-    const size_t n = (size_t)B * D;
+    const size_t n = (size_t)B * split_dp(D);
     if (n == 0) return cudaSuccess;
-    split_projections_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(W64, n, out);
+    uint16_t* out16 = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(out) + split_tf32_bytes(B, D));
+    split_projections_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(W64, B, D, split_dp(D), out, out16);
     count_launch();
     return cudaGetLastError();
 }
@@ -376,6 +565,19 @@ static bool make_tmap(CUtensorMap* tm, const float* ptr, unsigned long long rows
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// [rows, Dp] bfloat16 row-major, boxes of 64 elements x box_rows rows, 128-byte swizzle, zero fill
+static bool make_tmap_bf16(CUtensorMap* tm, const void* ptr, unsigned long long rows, uint32_t Dp, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t gdim[2] = {Dp, rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)Dp * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kPbKBlock, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool project_tc_applicable(unsigned long long N, uint32_t D, uint32_t B) {
     return N > 0 && D >= 4 && D % 4 == 0 && B % 64 == 0 && B >= 64 && B <= 65536 && N < (1ull << 47) &&
            encode_tiled_fn() != nullptr;
@@ -391,7 +593,7 @@ size_t project_tc_workspace_bytes(unsigned long long N, uint32_t B, uint32_t* fi
 
 cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, const float* Wsplit, const double* W64,
                               uint32_t B, float w_norm_max, uint64_t* out, void* ws, int sm_count, int smem_optin,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, bool use_bf16) {
     uint32_t fix_cap = 0;
     project_tc_workspace_bytes(N, B, &fix_cap);
     uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
@@ -412,23 +614,30 @@ cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, 
     p.num_ntiles = B / n_tile;
     p.num_mtiles = (N + kPtTileRows - 1) / kPtTileRows;
     p.fix_cap = fix_cap;
-    p.tol_scale = (8.0f + 0.25f * (float)D) / 4194304.0f * w_norm_max;   // eps = (8 + D/4) * 2^-22, see the header
-    const uint32_t stage_bytes = 2u * kPtAStage + 2u * n_tile * 128u;
+    // eps: (8 + D/4) * 2^-22 for the TF32 split, (52 + D/4) * 2^-22 for the BF16 split (see the kernels)
+    p.tol_scale = ((use_bf16 ? 52.0f : 8.0f) + 0.25f * (float)D) / 4194304.0f * w_norm_max;
+    const uint32_t stage_bytes = use_bf16 ? 4u * kPtAStage + 2u * n_tile * 128u : 2u * kPtAStage + 2u * n_tile * 128u;
     uint32_t stages = (uint32_t)((smem_optin - 2048) / (int)stage_bytes);
     if (stages > 4) stages = 4;
     if (stages < 2) return cudaErrorInvalidValue;
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
 
-    CUtensorMap tm_x, tm_w;   // tm_w: the split projections [2B, D] (wh rows, then wl rows)
-    if (!make_tmap(&tm_x, X, N, D, kPtTileRows) || !make_tmap(&tm_w, Wsplit, 2ull * B, D, n_tile))
+    CUtensorMap tm_x, tm_w;   // tm_w: the split projections [2B, D] (high rows, then low rows)
+    if (!make_tmap(&tm_x, X, N, D, kPtTileRows)) return cudaErrorInvalidValue;
+    if (use_bf16) {
+        const void* w16 = reinterpret_cast<const uint8_t*>(Wsplit) + split_tf32_bytes(B, D);
+        if (!make_tmap_bf16(&tm_w, w16, 2ull * B, split_dp(D), n_tile)) return cudaErrorInvalidValue;
+    } else if (!make_tmap(&tm_w, Wsplit, 2ull * B, D, n_tile)) {
         return cudaErrorInvalidValue;
+    }
 
     cudaError_t e = cudaMemsetAsync(fix_count, 0, 4, stream);
     if (e != cudaSuccess) return e;
     row_norm_kernel<<<(unsigned)((N + 7) / 8), 256, 0, stream>>>(X, N, D, norms);
     count_launch();
-    auto kern = n_tile == 128 ? project_tc_kernel<128> : project_tc_kernel<64>;
+    auto kern = use_bf16 ? (n_tile == 128 ? project_bf16_kernel<128> : project_bf16_kernel<64>)
+                         : (n_tile == 128 ? project_tc_kernel<128> : project_tc_kernel<64>);
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned long long items = p.num_mtiles * p.num_ntiles;

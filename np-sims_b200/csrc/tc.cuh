@@ -75,6 +75,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // kind::mxf4: E2M1 (4-bit) operands packed two per byte, K = 64 per instruction, block-32 UE8M0
 // scale factors read from TMEM.  Instruction descriptor (cute::UMMA::InstrDescriptorBlockScaled):
 __host__ __device__ constexpr uint32_t umma_idesc_mxf4(uint32_t M, uint32_t N) {

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libnpsims_b200.so")
 NPS_OK, NPS_EINVAL, NPS_ECUDA, NPS_EWORKSPACE = 0, -1, -2, -3
 NPS_MAX_K, NPS_MAX_WORDS = 2048, 1024
 ORDER_CANONICAL, ORDER_REFERENCE = 0, 1
+HASH_AUTO, HASH_TF32, HASH_BF16 = 0, 1, 2
 SCAN_AUTO, SCAN_POPC, SCAN_MMA = 0, 1, 2
 
 if not os.path.exists(LIB_PATH):
@@ -57,6 +58,8 @@ _SIGS = {
     "nps_rerank_top_n": (_int, [_vp, _u64, _u32, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp]),
     "nps_project_sign_pack_workspace_bytes": (_sz, [_u64, _u32]),
     "nps_project_split_projections": (_int, [_vp, _u32, _u32, _vp, _vp]),
+    "nps_project_split_bytes": (_sz, [_u32, _u32]),
+    "nps_set_hash_path": (_int, [_int]),
     "nps_project_sign_pack": (_int, [_vp, _u64, _u32, _vp, _vp, _u32, ctypes.c_float, _vp, _vp, _sz, _vp]),
     "nps_project_sign_pack_stats": (_int, [_vp, _u64, _u32, _vp, ctypes.POINTER(_u32), ctypes.POINTER(_u32)]),
     "nps_project_sign_pack_f64": (_int, [_vp, _int, _u64, _u32, _vp, _u32, _vp, _vp, _vp]),

@@ -72,7 +72,7 @@ def hash_stats():
     `overflowed` says the fix-up list was too small and the whole call was redone in float64 on
     the device.  Synchronises the stream; the hashing call itself never does."""
     st = dict(last_hash_stats)
-    if st["path"] == "tf32x3+fixup" and _last_hash_ws is not None:
+    if st["path"] == "tc-split+fixup" and _last_hash_ws is not None:
         import ctypes
         ws, n, b = _last_hash_ws
         fixed, cap = ctypes.c_uint32(0), ctypes.c_uint32(0)
@@ -82,13 +82,14 @@ def hash_stats():
 
 
 def _projections_split(projections, P64):
-    """[2, B, D] float32 TF32 split of the projections (nps_project_split_projections) and
+    """Both operand encodings of the projections (nps_project_split_projections: TF32 pair as
+    float32 [2, B, D], BF16 pair as bfloat16 [2, B, Dp]) and
     max_j |w_j| for the tensor-core pass, cached on the DeviceArray next to the float64 upload."""
     t = require_cuda()
     cached = getattr(projections, "_nps_dev32", None) if isinstance(projections, DeviceArray) else None
     if cached is not None:
         return cached
-    split = t.empty((2,) + tuple(P64.shape), dtype=t.float32, device=P64.device)
+    split = t.empty(_lib.raw("nps_project_split_bytes")(P64.shape[0], P64.shape[1]), dtype=t.uint8, device=P64.device)
     with t.cuda.device(P64.device):
         _lib.call("nps_project_split_projections", ptr(P64), P64.shape[0], P64.shape[1], ptr(split), stream_ptr())
     norm_max = float(t.linalg.vector_norm(P64, dim=1).max().item()) * (1.0 + 1e-6)
@@ -103,8 +104,8 @@ def hash_vectors(vectors, projections, return_dots=False, exact_only=False, tf32
     signatures (bit j = (projections[j] . x >= 0) at word j//64, bit j%64 — lsh.py:33).
 
     float32 vectors with D % 4 == 0 take the tensor-core path (K1T: TMA-fed tcgen05 GEMM on
-    two-term TF32 splits of both operands, sign/bit-pack epilogue, float64 fix-up of the ~0.1 % of
-    pairs whose accumulator is too close to zero); everything else, `return_dots` and
+    two-term BF16 (or TF32, `_lib.HASH_TF32`) splits of both operands, sign/bit-pack epilogue,
+    float64 fix-up of the ~0.04 % of pairs whose accumulator is too close to zero); everything else, `return_dots` and
     `exact_only` take the float64 CUDA-core kernel (K1a).  Both give the signatures of the
     reference's float64 arithmetic.  The call is asynchronous (no host sync).
     `tf32_raw=True` (measurement only) disables the fix-up, returning the bare tensor-core signs,
@@ -131,7 +132,7 @@ def hash_vectors(vectors, projections, return_dots=False, exact_only=False, tf32
             _lib.call("nps_project_sign_pack", ptr(X), n, d, ptr(split), ptr(P), b, 1e-30 if tf32_raw else norm_max,
                       ptr(out), ptr(ws), ws_bytes, stream_ptr())
             _last_hash_ws = (ws, n, b)
-            last_hash_stats.update(path="tf32x3+fixup", pairs=n * b, recomputed=None)
+            last_hash_stats.update(path="tc-split+fixup", pairs=n * b, recomputed=None)
             return out
         dots = t.empty((n, b), dtype=t.float64, device=P.device) if return_dots else None
         _lib.call("nps_project_sign_pack_f64", ptr(X), int(X.dtype == t.float32), n, d, ptr(P), b, ptr(out), ptr(dots),

@@ -344,11 +344,13 @@ def test_torch_tensor_inputs_stay_on_device(nps):
 @pytest.mark.parametrize("n,dims,bits", [(1, 300, 640), (127, 300, 640), (1019, 300, 640), (5000, 768, 1024),
                                          (3001, 100, 128), (2000, 52, 64), (4096, 300, 2560)])
 def test_tensor_core_hash_equals_float64_oracle(nps, n, dims, bits):
-    """K1T (tcgen05 GEMM on two-term TF32 splits + float64 fix-up) must give the oracle's float64
-    signatures; the bare tensor-core signs may only differ where |x.w| is below the stated
-    tolerance (8 + dims / 4) * 2^-22 * |x| * max|w|."""
+    """K1T (tcgen05 GEMM on two-term splits of both operands + float64 fix-up) must give the oracle's
+    float64 signatures with either operand encoding — BF16 x 2 (default) and TF32 x 2; the bare
+    tensor-core signs may only differ where |x.w| is below the stated tolerance
+    (c + dims / 4) * 2^-22 * |x| * max|w|, c = 52 (BF16) / 8 (TF32)."""
     import torch
     import np_sims.lsh as lsh
+    from np_sims import _lib
     rng = np.random.default_rng(n + dims)
     X = rng.standard_normal((n, dims)).astype(np.float32)
     X /= np.linalg.norm(X, axis=1, keepdims=True)
@@ -356,23 +358,27 @@ def test_tensor_core_hash_equals_float64_oracle(nps, n, dims, bits):
     np.random.seed(bits)
     W = lsh.create_projections(bits, dims)
     want = oracle.index_np(X, np.asarray(W))
-    got = lsh.index(X, W)
-    st = lsh.hash_stats()
-    assert st["path"] == "tf32x3+fixup" and not st["overflowed"]
-    assert np.array_equal(np.asarray(got), want)
-    frac = st["recomputed"] / st["pairs"]
-    assert frac < 0.02, frac
-    # bare TF32: flipped bits only where the float64 projection is inside the tolerance
-    raw = lsh.hash_vectors(torch.from_numpy(X).cuda(), W, tf32_raw=True).cpu().numpy().view(np.uint64)
-    flips = np.unpackbits((raw ^ want).view(np.uint8), bitorder="little").reshape(n, -1)[:, :bits].astype(bool)
     dots = X.astype(np.float64) @ np.asarray(W).T
     wmax = np.linalg.norm(np.asarray(W), axis=1).max()
-    tol = (8 + dims / 4) * 2.0 ** -22 * np.linalg.norm(X.astype(np.float64), axis=1, keepdims=True) * wmax * 1.0001
-    assert not np.any(flips & (np.abs(dots) >= tol)), "the tensor-core pass flipped a bit outside the stated tolerance"
-    # how much of the tolerance the tensor-core arithmetic actually uses: largest |dot| of a flipped bit
-    used = float((np.abs(dots) / tol)[flips].max()) if flips.any() else 0.0
-    print(f"K1T n={n} dims={dims} bits={bits}: raw flipped-bit rate {flips.mean():.2e} (largest flipped |x.w| = "
-          f"{used:.3f} of the tolerance), recomputed in float64 {frac:.3%}")
+    for path, name, c in ((_lib.HASH_BF16, "bf16x2", 52), (_lib.HASH_TF32, "tf32x2", 8)):
+        _lib.call("nps_set_hash_path", path)
+        try:
+            got = lsh.index(X, W)
+            st = lsh.hash_stats()
+            assert st["path"] == "tc-split+fixup" and not st["overflowed"]
+            assert np.array_equal(np.asarray(got), want), name
+            frac = st["recomputed"] / st["pairs"]
+            assert frac < 0.02, frac
+            # bare tensor-core pass: flipped bits only where the float64 projection is inside the tolerance
+            raw = lsh.hash_vectors(torch.from_numpy(X).cuda(), W, tf32_raw=True).cpu().numpy().view(np.uint64)
+        finally:
+            _lib.call("nps_set_hash_path", _lib.HASH_AUTO)
+        flips = np.unpackbits((raw ^ want).view(np.uint8), bitorder="little").reshape(n, -1)[:, :bits].astype(bool)
+        tol = (c + dims / 4) * 2.0 ** -22 * np.linalg.norm(X.astype(np.float64), axis=1, keepdims=True) * wmax * 1.0001
+        assert not np.any(flips & (np.abs(dots) >= tol)), f"{name}: flipped a bit outside the stated tolerance"
+        used = float((np.abs(dots) / tol)[flips].max()) if flips.any() else 0.0
+        print(f"K1T {name} n={n} dims={dims} bits={bits}: raw flipped-bit rate {flips.mean():.2e} (largest flipped "
+              f"|x.w| = {used:.3f} of the tolerance), recomputed in float64 {frac:.3%}")
 
 
 def test_tensor_core_hash_degenerate_inputs(nps):
@@ -385,7 +391,7 @@ def test_tensor_core_hash_degenerate_inputs(nps):
     got = lsh.index(X, W)
     assert np.array_equal(np.asarray(got), oracle.index_np(X, np.asarray(W)))
     st = lsh.hash_stats()           # every row is zero or tiny: all pairs listed, list overflows, and the
-    assert st["path"] == "tf32x3+fixup" and st["overflowed"]      # gated float64 launch redoes the call
+    assert st["path"] == "tc-split+fixup" and st["overflowed"]      # gated float64 launch redoes the call
     # a few wild rows among ordinary ones: only those rows go to the fix-up list
     rng = np.random.default_rng(9)
     X3 = rng.standard_normal((5000, 64)).astype(np.float32)
