@@ -89,9 +89,13 @@ __device__ __forceinline__ uint32_t tf32_low_part(uint32_t x) {
 // Epilogue shared by both operand encodings: signs of C1 + C2 -> uint64 words, uncertain entries ->
 // fix-up list (one atomic per warp and item).  Accumulator buffer b holds C1 at columns [2 NT b, +NT)
 // and C2 right behind it.
+// norm_s: null -> |x_i| comes from p.norms (row_norm_kernel); else the splitter warps left it in shared
+// memory, kPtNormBufs buffers of 128 floats indexed by the item count (BF16 kernel).
+constexpr uint32_t kPtNormBufs = 8;   // splitters run at most 2 + stages items ahead of the epilogue
 template <uint32_t NT>
 __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t tmem_base, uint64_t* acc_full,
-                                                 uint64_t* acc_empty, int warp, int lane, unsigned long long total) {
+                                                 uint64_t* acc_empty, int warp, int lane, unsigned long long total,
+                                                 const float* norm_s = nullptr) {
         const uint32_t quarter = warp & 3u;
         const uint32_t r_in_tile = quarter * 32u + lane;
         const uint32_t words_per_row = p.B / 64u;
@@ -103,11 +107,13 @@ __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t
             const uint32_t buf = t_idx & 1u;
             const unsigned long long row = mt * kPtTileRows + r_in_tile;
             const bool valid = row < p.N;
-            const float norm = valid ? __ldg(p.norms + row) : 1.f;
-            const bool tame = norm >= 1e-18f && norm <= 1e18f;     // false for 0, tiny, huge, inf, NaN
-            const float tol = p.tol_scale * norm;
+            float norm = (valid && norm_s == nullptr) ? __ldg(p.norms + row) : 1.f;
             mbar_wait(&acc_full[buf], (t_idx >> 1) & 1u);
             tc_fence_after();
+            if (valid && norm_s != nullptr)      // written before the splitters' last split_done of the item
+                norm = reinterpret_cast<const volatile float*>(norm_s)[(t_idx % kPtNormBufs) * kPtTileRows + r_in_tile];
+            const bool tame = norm >= 1e-18f && norm <= 1e18f;     // false for 0, tiny, huge, inf, NaN
+            const float tol = p.tol_scale * norm;
             const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * (2u * NT);
             uint32_t sign_m[G], unsure_m[G];
 #pragma unroll
@@ -339,6 +345,7 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     uint64_t* acc_full = empty + S;     // [2]
     uint64_t* acc_empty = acc_full + 2; // [2]
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* norm_s = reinterpret_cast<float*>(tmem_ptr_s + 4);   // [kPtNormBufs][128]: |x_i| from the splitters
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -423,8 +430,9 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         // chunk index XORed by (row & 7): conflict-free for the eight rows of a quarter warp.
         const uint32_t r = (uint32_t)tid - 192u, r7 = r & 7u;
         const uint32_t rowoff = (r >> 3) * 1024u + r7 * 128u;
-        uint32_t s = 0, ph = 0;
-        for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x) {
+        uint32_t s = 0, ph = 0, t_idx = 0;
+        for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx) {
+            float sumsq = 0.f;      // this row sees all of its D floats pass by: |x_i| for free (no norm kernel)
             for (uint32_t kb = 0; kb < KB; ++kb) {
                 mbar_wait(&full[s], ph);
                 uint8_t* st = smem + s * stage_bytes;
@@ -439,9 +447,12 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                     split_bf16x2(a.z, a.w, h.y, l.y);
                     split_bf16x2(b.x, b.y, h.z, l.z);
                     split_bf16x2(b.z, b.w, h.w, l.w);
+                    sumsq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, sumsq))));
+                    sumsq = fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(b.z, b.z, fmaf(b.w, b.w, sumsq))));
                     *reinterpret_cast<uint4*>(st + kRaw + rowoff + ((j ^ r7) << 4)) = h;
                     *reinterpret_cast<uint4*>(st + kRaw + kOp + rowoff + ((j ^ r7) << 4)) = l;
                 }
+                if (kb + 1 == KB) norm_s[(t_idx % kPtNormBufs) * kPtTileRows + r] = sqrtf(sumsq) * 1.001f;
                 fence_proxy_async_smem();   // generic-proxy stores -> visible to tcgen05.mma (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&split_done[s]);
@@ -452,7 +463,7 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             }
         }
     } else {
-        project_epilogue<NT>(p, tmem_base, acc_full, acc_empty, warp, lane, total);
+        project_epilogue<NT>(p, tmem_base, acc_full, acc_empty, warp, lane, total, norm_s);
     }
     tc_fence_before();
     __syncthreads();
@@ -621,7 +632,7 @@ cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, 
     if (stages > 4) stages = 4;
     if (stages < 2) return cudaErrorInvalidValue;
     p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + (use_bf16 ? kPtNormBufs * kPtTileRows * 4 : 0);
 
     CUtensorMap tm_x, tm_w;   // tm_w: the split projections [2B, D] (high rows, then low rows)
     if (!make_tmap(&tm_x, X, N, D, kPtTileRows)) return cudaErrorInvalidValue;
@@ -634,8 +645,10 @@ cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, 
 
     cudaError_t e = cudaMemsetAsync(fix_count, 0, 4, stream);
     if (e != cudaSuccess) return e;
-    row_norm_kernel<<<(unsigned)((N + 7) / 8), 256, 0, stream>>>(X, N, D, norms);
-    count_launch();
+    if (!use_bf16) {   // the BF16 kernel's splitter warps compute |x_i| on the way
+        row_norm_kernel<<<(unsigned)((N + 7) / 8), 256, 0, stream>>>(X, N, D, norms);
+        count_launch();
+    }
     auto kern = use_bf16 ? (n_tile == 128 ? project_bf16_kernel<128> : project_bf16_kernel<64>)
                          : (n_tile == 128 ? project_tc_kernel<128> : project_tc_kernel<64>);
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
