@@ -46,6 +46,8 @@ def _compile(unit, force: bool, verbose: bool):
         return obj, False
     if os.environ.get("NPS_DEV"):      # development build: event trace + cycle accounting in mma_scan.cu
         defs = [*defs, "-DNPS_MMA_DEV"]
+    if os.environ.get("NPS_KNOBS"):    # host-side development knobs (NPS_MMA_* environment variables) only
+        defs = [*defs, "-DNPS_MMA_KNOBS"]
     cmd = [NVCC, *FLAGS, *defs, "-c", src_path, "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -850,6 +850,18 @@ cudaError_t launch_mma_select(const MmaSelectParams& p, cudaStream_t stream, boo
 }
 
 
+// Development knobs (schedule sweeps, traces, PDL on/off) are environment variables that exist only
+// in builds made with NPS_KNOBS=1 or NPS_DEV=1 (np-sims_b200/build.py); a production build never
+// reads the environment.
+static inline const char* dev_knob(const char* name) {
+#if defined(NPS_MMA_KNOBS) || defined(NPS_MMA_DEV)
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
+
 // =============================================================================================
 // host: plan + phase loop
 // =============================================================================================
@@ -891,7 +903,7 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
         if (n_tile || gs == 1) break;
     }
     if (!n_tile) return false;
-    if (const char* e = getenv("NPS_MMA_GROUPS")) {     // development: "GS,RG"
+    if (const char* e = dev_knob("NPS_MMA_GROUPS")) {     // development: "GS,RG"
         uint32_t gs = 0, rg = 0;
         if (sscanf(e, "%u,%u", &gs, &rg) == 2 && gs && (rg == 1 || rg == 2)) {
             gs_best = gs;
@@ -913,8 +925,8 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
     uint32_t growth = cap / (4u * k);
     if (growth > 8u) growth = 8u;
     if (growth < 2u) growth = 2u;
-    if (const char* e = getenv("NPS_MMA_CAP")) cap = (uint32_t)atoi(e);          // development
-    if (const char* e = getenv("NPS_MMA_GROWTH")) growth = (uint32_t)atoi(e);    // development
+    if (const char* e = dev_knob("NPS_MMA_CAP")) cap = (uint32_t)atoi(e);          // development
+    if (const char* e = dev_knob("NPS_MMA_GROWTH")) growth = (uint32_t)atoi(e);    // development
     pl->cap = cap;
     pl->growth = growth;
     pl->sort_cap = pow2_ceil(k + cap);
@@ -935,7 +947,7 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
     exps[np++] = e0;
     for (uint32_t e = e0; e > 0;) {
         uint32_t late = 3;   // number of final phases that only double
-        if (const char* ev = getenv("NPS_MMA_LATE")) late = (uint32_t)atoi(ev);   // development
+        if (const char* ev = dev_knob("NPS_MMA_LATE")) late = (uint32_t)atoi(ev);   // development
         const uint32_t step = e <= late ? 1u : (e - late < gshift ? e - late : gshift);
         e -= step;
         if (np == kMmaMaxPhases) return false;
@@ -1009,7 +1021,7 @@ cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned 
     if (e != cudaSuccess) return e;
     // Programmatic dependent launch between the back-to-back scan / select launches, unless per-phase
     // events are being recorded between them (profiling) or NPS_NO_PDL is set (development).
-    const bool use_pdl = phase_events == nullptr && getenv("NPS_NO_PDL") == nullptr;
+    const bool use_pdl = phase_events == nullptr && dev_knob("NPS_NO_PDL") == nullptr;
     for (uint32_t ph = 0; ph < pl.num_phases; ++ph) {
         const MmaPhase& P = pl.phase[ph];
         const bool last = ph + 1 == pl.num_phases;
@@ -1040,14 +1052,14 @@ cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned 
             sp.group_kb = pl.group_kb;
             sp.ring_per_issuer = pl.ring_per_issuer;
             sp.trace = nullptr;
-            const char* trace_path = getenv("NPS_MMA_TRACE");
-            const char* trace_phase = getenv("NPS_MMA_TRACE_PHASE");
+            const char* trace_path = dev_knob("NPS_MMA_TRACE");
+            const char* trace_phase = dev_knob("NPS_MMA_TRACE_PHASE");
             if (trace_path && (trace_phase ? (uint32_t)atoi(trace_phase) == ph : last)) {
                 cudaMalloc(&sp.trace, 4 * 4096 * 16);
                 cudaMemsetAsync(sp.trace, 0, 4 * 4096 * 16, stream);
             }
             {
-                const char* dbg = getenv("NPS_MMA_DEBUG");
+                const char* dbg = dev_knob("NPS_MMA_DEBUG");
                 sp.debug = (dbg && !sp.dense) ? (uint32_t)atoi(dbg) : 0u;
             }
             if (phase_events) {
