@@ -326,33 +326,47 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& h, uint
     l = pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xFFFF0000u));
 }
 
+// Rings: raw X (kPbRawSlots x 32 KB float32: dead as soon as it is split, so it has its own, deeper
+// look-ahead) and operands (S x [x0 16 KB | x1 16 KB | w0 | w1]).  Two producer threads (X and W) so that
+// neither waits on the other's ring.
+constexpr uint32_t kPbRawSlots = 2;
+constexpr int kPbThreads = 11 * 32;     // X producer, MMA issuer, 4 epilogue warps, 4 splitter warps, W producer
+
 template <uint32_t NT>
-__global__ void __launch_bounds__(kPtThreads, 1)
+__global__ void __launch_bounds__(kPbThreads, 1)
 project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                     const ProjTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw);
-    const uint32_t S = p.stages;
+    const uint32_t S = p.stages;                                // operand slots
+    constexpr uint32_t R = kPbRawSlots;
     constexpr uint32_t kWTile = NT * 128u;                      // NT projections x 64 bf16
     constexpr uint32_t kRaw = 2u * kPtAStage, kOp = kPtAStage;  // 32 KB raw, 16 KB per bf16 X tile
-    constexpr uint32_t stage_bytes = kRaw + 2u * kOp + 2u * kWTile;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
-    uint64_t* full = bars;
-    uint64_t* split_done = full + S;
-    uint64_t* empty = split_done + S;
-    uint64_t* acc_full = empty + S;     // [2]
-    uint64_t* acc_empty = acc_full + 2; // [2]
+    constexpr uint32_t op_bytes = 2u * kOp + 2u * kWTile;
+    const uint32_t op_base = R * kRaw;                          // operand ring behind the raw ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + op_base + S * op_bytes);
+    uint64_t* raw_full = bars;              // [R] TMA landed the float32 tile
+    uint64_t* raw_empty = raw_full + R;     // [R] splitters are done with it
+    uint64_t* w_full = raw_empty + R;       // [S] TMA landed w0, w1
+    uint64_t* split_done = w_full + S;      // [S] splitters wrote x0, x1
+    uint64_t* op_empty = split_done + S;    // [S] MMAs of the slot retired
+    uint64_t* acc_full = op_empty + S;      // [2]
+    uint64_t* acc_empty = acc_full + 2;     // [2]
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* norm_s = reinterpret_cast<float*>(tmem_ptr_s + 4);   // [kPtNormBufs][128]: |x_i| from the splitters
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
+        for (uint32_t s = 0; s < R; ++s) {
+            mbar_init(&raw_full[s], 1);
+            mbar_init(&raw_empty[s], 4);
+        }
         for (uint32_t s = 0; s < S; ++s) {
-            mbar_init(&full[s], 1);
+            mbar_init(&w_full[s], 1);
             mbar_init(&split_done[s], 4);
-            mbar_init(&empty[s], 1);
+            mbar_init(&op_empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
@@ -370,20 +384,37 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     const unsigned long long total = p.num_mtiles * p.num_ntiles;
 
     if (warp == 0) {
-        // ===== TMA producer
+        // ===== X producer: two 32-float boxes per K-block into the raw ring
+        if (lane == 0) {
+            uint32_t rs = 0, rph = 0;
+            for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x) {
+                const unsigned long long mt = item / p.num_ntiles;
+                for (uint32_t kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&raw_empty[rs], rph ^ 1u);
+                    const uint32_t dst = base + rs * kRaw;
+                    mbar_arrive_expect_tx(&raw_full[rs], kRaw);
+                    tma_load_2d(dst, &tm_x, kb * kPbKBlock, (uint32_t)(mt * kPtTileRows), &raw_full[rs]);
+                    tma_load_2d(dst + kPtAStage, &tm_x, kb * kPbKBlock + 32u, (uint32_t)(mt * kPtTileRows), &raw_full[rs]);
+                    if (++rs == R) {
+                        rs = 0;
+                        rph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 10) {
+        // ===== W producer: w0 and w1 tiles straight into the operand slot
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
             for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x) {
                 const unsigned long long mt = item / p.num_ntiles;
                 const uint32_t nt = (uint32_t)(item - mt * p.num_ntiles);
                 for (uint32_t kb = 0; kb < KB; ++kb) {
-                    mbar_wait(&empty[s], ph ^ 1u);
-                    const uint32_t dst = base + s * stage_bytes;
-                    mbar_arrive_expect_tx(&full[s], kRaw + 2u * kWTile);
-                    tma_load_2d(dst, &tm_x, kb * kPbKBlock, (uint32_t)(mt * kPtTileRows), &full[s]);
-                    tma_load_2d(dst + kPtAStage, &tm_x, kb * kPbKBlock + 32u, (uint32_t)(mt * kPtTileRows), &full[s]);
-                    tma_load_2d(dst + kRaw + 2u * kOp, &tm_w, kb * kPbKBlock, nt * NT, &full[s]);
-                    tma_load_2d(dst + kRaw + 2u * kOp + kWTile, &tm_w, kb * kPbKBlock, p.B + nt * NT, &full[s]);
+                    mbar_wait(&op_empty[s], ph ^ 1u);
+                    const uint32_t dst = base + op_base + s * op_bytes + 2u * kOp;
+                    mbar_arrive_expect_tx(&w_full[s], 2u * kWTile);
+                    tma_load_2d(dst, &tm_w, kb * kPbKBlock, nt * NT, &w_full[s]);
+                    tma_load_2d(dst + kWTile, &tm_w, kb * kPbKBlock, p.B + nt * NT, &w_full[s]);
                     if (++s == S) {
                         s = 0;
                         ph ^= 1u;
@@ -402,19 +433,19 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             tc_fence_after();
             const uint32_t c1 = tmem_base + buf * (2u * NT), c2 = c1 + NT;
             for (uint32_t kb = 0; kb < KB; ++kb) {
-                mbar_wait(&full[s], ph);
+                mbar_wait(&w_full[s], ph);
                 mbar_wait(&split_done[s], ph);
                 tc_fence_after();
                 if (pt_elect_one()) {
-                    const uint32_t st = base + s * stage_bytes;
-                    const uint64_t x0 = umma_desc_k_sw128(st + kRaw), x1 = umma_desc_k_sw128(st + kRaw + kOp);
-                    const uint64_t w0 = umma_desc_k_sw128(st + kRaw + 2u * kOp);   // w1 follows at + kWTile
+                    const uint32_t st = base + op_base + s * op_bytes;
+                    const uint64_t x0 = umma_desc_k_sw128(st), x1 = umma_desc_k_sw128(st + kOp);
+                    const uint64_t w0 = umma_desc_k_sw128(st + 2u * kOp);   // w1 follows at + kWTile
 #pragma unroll
                     for (uint32_t j = 0; j < 4; ++j) {   // K = 16 bf16 (32 bytes) per instruction
                         umma_f16(c1, x0 + 2u * j, w0 + 2u * j, idesc2, (kb | j) != 0u);
                         umma_f16(c2, x1 + 2u * j, w0 + 2u * j, idesc, true);
                     }
-                    umma_commit(&empty[s]);
+                    umma_commit(&op_empty[s]);
                     if (kb + 1 == KB) umma_commit(&acc_full[buf]);
                 }
                 __syncwarp();
@@ -430,15 +461,17 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         // chunk index XORed by (row & 7): conflict-free for the eight rows of a quarter warp.
         const uint32_t r = (uint32_t)tid - 192u, r7 = r & 7u;
         const uint32_t rowoff = (r >> 3) * 1024u + r7 * 128u;
-        uint32_t s = 0, ph = 0, t_idx = 0;
+        uint32_t s = 0, ph = 0, rs = 0, rph = 0, t_idx = 0;
         for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx) {
             float sumsq = 0.f;      // this row sees all of its D floats pass by: |x_i| for free (no norm kernel)
             for (uint32_t kb = 0; kb < KB; ++kb) {
-                mbar_wait(&full[s], ph);
-                uint8_t* st = smem + s * stage_bytes;
+                mbar_wait(&raw_full[rs], rph);
+                mbar_wait(&op_empty[s], ph ^ 1u);          // the slot's previous MMAs retired
+                const uint8_t* rawp = smem + rs * kRaw;
+                uint8_t* st = smem + op_base + s * op_bytes;
 #pragma unroll
                 for (uint32_t j = 0; j < 8; ++j) {
-                    const uint8_t* box = st + (j >> 2) * kPtAStage + rowoff;
+                    const uint8_t* box = rawp + (j >> 2) * kPtAStage + rowoff;
                     const uint32_t c0 = 2u * (j & 3u);
                     const float4 a = *reinterpret_cast<const float4*>(box + ((c0 ^ r7) << 4));
                     const float4 b = *reinterpret_cast<const float4*>(box + (((c0 + 1u) ^ r7) << 4));
@@ -449,13 +482,20 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                     split_bf16x2(b.z, b.w, h.w, l.w);
                     sumsq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, sumsq))));
                     sumsq = fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(b.z, b.z, fmaf(b.w, b.w, sumsq))));
-                    *reinterpret_cast<uint4*>(st + kRaw + rowoff + ((j ^ r7) << 4)) = h;
-                    *reinterpret_cast<uint4*>(st + kRaw + kOp + rowoff + ((j ^ r7) << 4)) = l;
+                    *reinterpret_cast<uint4*>(st + rowoff + ((j ^ r7) << 4)) = h;
+                    *reinterpret_cast<uint4*>(st + kOp + rowoff + ((j ^ r7) << 4)) = l;
                 }
                 if (kb + 1 == KB) norm_s[(t_idx % kPtNormBufs) * kPtTileRows + r] = sqrtf(sumsq) * 1.001f;
                 fence_proxy_async_smem();   // generic-proxy stores -> visible to tcgen05.mma (async proxy)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&split_done[s]);
+                if (lane == 0) {
+                    mbar_arrive(&raw_empty[rs]);
+                    mbar_arrive(&split_done[s]);
+                }
+                if (++rs == R) {
+                    rs = 0;
+                    rph ^= 1u;
+                }
                 if (++s == S) {
                     s = 0;
                     ph ^= 1u;
@@ -627,12 +667,14 @@ cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, 
     p.fix_cap = fix_cap;
     // eps: (8 + D/4) * 2^-22 for the TF32 split, (52 + D/4) * 2^-22 for the BF16 split (see the kernels)
     p.tol_scale = ((use_bf16 ? 52.0f : 8.0f) + 0.25f * (float)D) / 4194304.0f * w_norm_max;
-    const uint32_t stage_bytes = use_bf16 ? 4u * kPtAStage + 2u * n_tile * 128u : 2u * kPtAStage + 2u * n_tile * 128u;
-    uint32_t stages = (uint32_t)((smem_optin - 2048) / (int)stage_bytes);
+    // TF32: stages of [xh | xl | wh | wl]; BF16: a raw-X ring of kPbRawSlots x 32 KB + operand slots [x0 | x1 | w0 | w1]
+    const uint32_t stage_bytes = 2u * kPtAStage + 2u * n_tile * 128u;
+    const uint32_t fixed = use_bf16 ? kPbRawSlots * 2u * kPtAStage + kPtNormBufs * kPtTileRows * 4u : 0u;
+    uint32_t stages = (uint32_t)((smem_optin - 2048 - (int)fixed) / (int)stage_bytes);
     if (stages > 4) stages = 4;
     if (stages < 2) return cudaErrorInvalidValue;
     p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + (use_bf16 ? kPtNormBufs * kPtTileRows * 4 : 0);
+    const size_t smem = (size_t)stages * stage_bytes + fixed + 1024 + 512;
 
     CUtensorMap tm_x, tm_w;   // tm_w: the split projections [2B, D] (high rows, then low rows)
     if (!make_tmap(&tm_x, X, N, D, kPtTileRows)) return cudaErrorInvalidValue;
@@ -655,7 +697,7 @@ cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, 
     if (e != cudaSuccess) return e;
     const unsigned long long items = p.num_mtiles * p.num_ntiles;
     const int grid = (int)(items < (unsigned long long)sm_count ? items : (unsigned long long)sm_count);
-    kern<<<grid, kPtThreads, smem, stream>>>(tm_x, tm_w, p);
+    kern<<<grid, use_bf16 ? kPbThreads : kPtThreads, smem, stream>>>(tm_x, tm_w, p);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
