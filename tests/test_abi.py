@@ -86,3 +86,14 @@ def test_errors_without_gpu_match_reference_types():
         np_sims.hamming_top_10(h, h[0])
     with pytest.raises(ValueError, match="multiple of 64"):
         lsh.index(np.zeros((3, 8)), np.zeros((100, 8)))
+
+
+def test_hash_split_buffer_size_and_path_switch_need_no_gpu():
+    from np_sims import _lib
+    size = _lib.raw("nps_project_split_bytes")(640, 300)
+    tf32 = (2 * 640 * 300 * 4 + 255) // 256 * 256              # float32 [2, B, D]
+    assert size == tf32 + 2 * 640 * 304 * 2                    # + bfloat16 [2, B, D rounded up to 8]
+    assert _lib.raw("nps_set_hash_path")(7) != 0 and "hash path" in _lib.last_error()
+    for path in (_lib.HASH_TF32, _lib.HASH_BF16, _lib.HASH_AUTO):
+        assert _lib.raw("nps_set_hash_path")(path) == 0
+    assert _lib.raw("nps_set_scan_path")(9) != 0
