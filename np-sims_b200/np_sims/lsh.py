@@ -173,13 +173,27 @@ def _as_index_dtype(ids):
     return ids.view(np.int64) if isinstance(ids, np.ndarray) else ids
 
 
+def _query_signature(vector, projections):
+    """Signature of ONE query vector, left on the device: hashing feeds the scan without the
+    D2H + H2D hop (and the synchronisation) that returning it as NumPy in between would cost."""
+    return hash_vectors(vector, projections)[0]
+
+
+def _results_like_inputs(out, vector, hashes):
+    """NumPy in -> NumPy out (the reference's contract); tensors stay tensors."""
+    if is_tensor(vector) or is_tensor(hashes):
+        return out
+    return to_host_u64(out) if is_tensor(out) else out
+
+
 def query_with_hamming_then_slow_argsort(vector, hashes, projections, hamming_func=hamming_c, n=10):
     """lsh.py:47-56 — distances then argsort()[:n]; returns (idxs, distances).  Here the
     selection is the stable (distance, row) order, done on the device."""
     _check_hamming_func(hamming_func)
-    query_hash = index_one(vector, projections)
+    query_hash = _query_signature(vector, projections)
     idxs, sims = hamming_top_n(hashes, query_hash, n=min(int(n), max(len(hashes), 1)), return_distances=True)
     keep = min(int(n), len(hashes))
+    idxs, sims = _results_like_inputs(idxs, vector, hashes), _results_like_inputs(sims, vector, hashes)
     return _as_index_dtype(idxs[:keep]), sims[:keep]
 
 
@@ -191,9 +205,9 @@ def query_pure_python(vector, hashes, projections, hamming_func=hamming_naive, n
 def query_with_hamming_top_n(vector, hashes, projections, hamming_func=hamming_c, n=10):
     """lsh.py:70-74 — (hamming_top_10 ids, None); `n` and `hamming_func` are ignored by the
     reference and therefore here."""
-    query_hash = index_one(vector, projections)
+    query_hash = _query_signature(vector, projections)
     best = hamming_top_10(hashes, query_hash)
-    return best, None
+    return _results_like_inputs(best, vector, hashes), None
 
 
 def front_hashes(hashes, front_bits=64):
