@@ -86,11 +86,16 @@ __device__ __forceinline__ void warp_sort_list(uint32_t* list, uint32_t cap, int
 }
 
 // Sort the list, keep the k best.  Returns the new element count; *tau_out = k-th key if full.
+// Only the smallest power of two >= cnt (>= 64) is sorted: the early refreshes of tau (below) handle
+// short lists.
 __device__ __forceinline__ uint32_t warp_compact(uint32_t* list, uint32_t cnt, uint32_t k, uint32_t cap, int lane,
                                                  uint32_t* tau_out) {
-    for (uint32_t i = cnt + lane; i < cap; i += 32) list[i] = kEmptyKey;
+    uint32_t n = 64;
+    while (n < cnt) n <<= 1;
+    if (n > cap) n = cap;
+    for (uint32_t i = cnt + lane; i < n; i += 32) list[i] = kEmptyKey;
     __syncwarp();
-    warp_sort_list(list, cap, lane);
+    warp_sort_list(list, n, lane);
     if (cnt >= k) {
         *tau_out = ((volatile uint32_t*)list)[k - 1];
         return k;
@@ -127,8 +132,12 @@ __device__ __noinline__ void append_candidates(uint32_t* list, uint32_t* tau_p, 
         cnt += n;
         __syncwarp();
     }
-    // Tighten tau as soon as k candidates exist, so the steady-state filter engages early.
-    if (cnt >= k && tau == kEmptyKey) cnt = warp_compact(list, cnt, k, cap, lane, &tau);
+    // Tighten tau as soon as k candidates exist, and again whenever k more have arrived: tau is what
+    // every warp filters with, and a threshold that is refreshed only when the list is full (cap - k
+    // appends later) stays at the k-th best of the first few thousand rows for the rest of the chunk —
+    // measured on a single-query scan: ~5 lock-serialised appends per tile, 0.3 ms for a 16 M-row table
+    // whatever the signature width (128 MB .. 1.3 GB), i.e. bound by this path and not by HBM.
+    if (cnt >= k && (tau == kEmptyKey || cnt >= 2u * k)) cnt = warp_compact(list, cnt, k, cap, lane, &tau);
     __syncwarp();
     if (lane == 0) {
         sts32_volatile(cnt_p, cnt);
