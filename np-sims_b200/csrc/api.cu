@@ -84,7 +84,7 @@ static int profile_events() {
 struct ScanPlan {
     bool specialised;
     uint32_t tile_rows, tile_bytes, stages, q_tile, num_qtiles, chunk_rows, num_chunks, cap, row_bits;
-    uint32_t smem;
+    uint32_t smem, lists_per_q;
     int grid;
 };
 
@@ -168,7 +168,11 @@ static int plan_scan(uint64_t N, uint32_t W, uint32_t Q, uint32_t k, int sm_coun
     const uint64_t items = (uint64_t)pl->num_chunks * pl->num_qtiles;
     if (items > 0xFFFFFFFFull) return fail(NPS_EINVAL, "too many work items");
     pl->grid = (int)(items < (uint64_t)sm_count ? items : (uint64_t)sm_count);
-    pl->smem = scan_smem_layout(pl->tile_bytes, pl->stages, W, pl->q_tile, cap).total;
+    // One or two queries (the single-query scan): one shared list per query means eight consumer warps
+    // on one lock; give every warp its own list (merged at the end of the work item).  From ~4 queries
+    // on the eight-fold appends of the private lists cost more than the lock (measured).
+    pl->lists_per_q = (pl->specialised && pl->q_tile <= 2 && cap == 64 && k <= 32) ? (uint32_t)kConsumerWarps : 1u;
+    pl->smem = scan_smem_layout(pl->tile_bytes, pl->stages, W, pl->q_tile, cap, pl->lists_per_q).total;
     if ((int)pl->smem > smem_optin) return fail(NPS_EINVAL, "internal: smem plan %u > %d", pl->smem, smem_optin);
     return NPS_OK;
 }
@@ -227,6 +231,7 @@ static int run_popc(const ScanPlan& pl, const uint64_t* d_hashes, uint64_t N, ui
     p.row_bits = pl.row_bits;
     p.stages = pl.stages;
     p.tile_rows = pl.tile_rows;
+    p.lists_per_q = pl.lists_per_q;
     if (profile) NPS_CUDA(cudaEventRecord(g_ev[0], stream));
     if (pl.specialised) {
         ScanLaunchFn fn = scan_launcher_for_width((int)W);

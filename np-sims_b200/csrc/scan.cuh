@@ -36,6 +36,7 @@ struct ScanParams {
     uint32_t row_bits;         // key = dist << row_bits | row_in_chunk
     uint32_t stages;
     uint32_t tile_rows;        // generic-width kernel only
+    uint32_t lists_per_q;      // 1: one shared (locked) candidate list per query; kConsumerWarps: one per warp
 };
 
 // Shared-memory carve-up, shared by host (sizing) and device.
@@ -44,7 +45,7 @@ struct ScanSmem {
 };
 __host__ __device__ inline uint32_t scan_q_stride(uint32_t words) { return ((words + 1) / 2 + 8) * 16; }
 __host__ __device__ inline ScanSmem scan_smem_layout(uint32_t tile_bytes, uint32_t stages, uint32_t words,
-                                                     uint32_t q_tile, uint32_t cap) {
+                                                     uint32_t q_tile, uint32_t cap, uint32_t lists_per_q = 1) {
     ScanSmem s;
     uint32_t off = 0;
     s.stage_off = off;
@@ -52,13 +53,13 @@ __host__ __device__ inline ScanSmem scan_smem_layout(uint32_t tile_bytes, uint32
     s.q_off = off;
     off += q_tile * scan_q_stride(words);
     s.list_off = off;
-    off += q_tile * cap * 4;
+    off += q_tile * lists_per_q * cap * 4;
     s.tau_off = off;
-    off += q_tile * 4;
+    off += q_tile * lists_per_q * 4;
     s.cnt_off = off;
-    off += q_tile * 4;
+    off += q_tile * lists_per_q * 4;
     s.lock_off = off;
-    off += q_tile * 4;
+    off += q_tile * lists_per_q * 4;
     off = (off + 7u) & ~7u;
     s.bar_off = off;
     off += stages * 16;
@@ -198,7 +199,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
 
     if (p.gate != nullptr && *p.gate == 0u) return;   // gated repair launch, nothing to repair
     extern __shared__ __align__(128) uint8_t smem[];
-    const ScanSmem L = scan_smem_layout(TILE_BYTES, p.stages, W, p.q_tile, p.cap);
+    const uint32_t LPQ = p.lists_per_q;   // > 1: every consumer warp owns a private list per query (no lock contention)
+    const ScanSmem L = scan_smem_layout(TILE_BYTES, p.stages, W, p.q_tile, p.cap, LPQ);
     uint8_t* stage_base = smem + L.stage_off;
     const uint32_t stage_stride = (TILE_BYTES + 127u) & ~127u;
     uint8_t* q_s = smem + L.q_off;
@@ -250,12 +252,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             val.y = (2 * vv + 1 < W) ? src[2 * vv + 1] : 0ull;
             *reinterpret_cast<ulonglong2*>(q_s + q * QSTRIDE + v * 16) = val;
         }
-        for (uint32_t q = tid; q < nq; q += kConsumerThreads) {
+        for (uint32_t q = tid; q < nq * LPQ; q += kConsumerThreads) {
             tau_s[q] = kEmptyKey;
             cnt_s[q] = 0;
             lock_s[q] = 0;
         }
         consumer_bar();
+        const uint32_t my_list = LPQ > 1 ? (uint32_t)warp : 0u;   // list (q, my_list) of query q
 
         uint32_t tile_row = 0;  // row offset of the current tile inside the chunk
         for (unsigned long long r0 = row0; r0 < row1; r0 += TILE_ROWS, tile_row += TILE_ROWS) {
@@ -305,7 +308,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             // ---- sweep the query tile
             uint32_t qaddr = q_base;
             for (uint32_t q = 0; q < nq; ++q, qaddr += QSTRIDE) {
-                const uint32_t tau = lds32_volatile(&tau_s[q]);
+                const uint32_t li = q * LPQ + my_list;
+                const uint32_t tau = lds32_volatile(&tau_s[li]);
                 uint32_t d[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) d[r] = 0;
@@ -327,17 +331,55 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
                     hit |= key[r] < tau;
                 }
                 if (__any_sync(0xffffffffu, hit))
-                    append_candidates<R>(list_s + q * cap, &tau_s[q], &cnt_s[q], &lock_s[q], key, valid_mask, k, cap,
+                    append_candidates<R>(list_s + li * cap, &tau_s[li], &cnt_s[li], &lock_s[li], key, valid_mask, k, cap,
                                          lane);
             }
         }
 
         // ---- item done: sort every list, emit k keys per query as dist<<40 | global row
         consumer_bar();
+        if (LPQ > 1) {
+            // private lists: every warp sorts its own, then one warp per query merges the LPQ k-prefixes
+            // (LPQ * k <= 256 keys) in the query's block of lists and leaves the result in list (q, 0)
+            for (uint32_t q = 0; q < nq; ++q) {
+                const uint32_t li = q * LPQ + (uint32_t)warp;
+                uint32_t tau_unused;
+                const uint32_t c = warp_compact(list_s + li * cap, cnt_s[li], k, cap, lane, &tau_unused);
+                if (lane == 0) cnt_s[li] = c;
+            }
+            consumer_bar();
+            for (uint32_t q = warp; q < nq; q += kConsumerWarps) {
+                uint32_t* block = list_s + q * LPQ * cap;
+                const uint32_t total = LPQ * k;                 // <= 256
+                uint32_t vals[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t e = (uint32_t)j * 32u + lane;
+                    const uint32_t src = e / k, idx = e - src * k;
+                    vals[j] = (e < total && idx < cnt_s[q * LPQ + src]) ? block[src * cap + idx] : kEmptyKey;
+                }
+                __syncwarp();
+                uint32_t n = 64;
+                while (n < total) n <<= 1;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t e = (uint32_t)j * 32u + lane;
+                    if (e < n) block[e] = vals[j];
+                }
+                __syncwarp();
+                warp_sort_list(block, n, lane);
+                uint32_t c = 0;
+                for (uint32_t i = lane; i < k; i += 32) c += block[i] != kEmptyKey;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                if (lane == 0) cnt_s[q * LPQ] = c;
+                __syncwarp();
+            }
+        }
         for (uint32_t q = warp; q < nq; q += kConsumerWarps) {
-            uint32_t* list = list_s + q * cap;
+            uint32_t* list = list_s + q * LPQ * cap;
             uint32_t tau_unused;
-            const uint32_t cnt = warp_compact(list, cnt_s[q], k, cap, lane, &tau_unused);
+            const uint32_t cnt = LPQ > 1 ? cnt_s[q * LPQ] : warp_compact(list, cnt_s[q], k, cap, lane, &tau_unused);
             uint64_t* out = p.out_keys + ((unsigned long long)(q0 + q) * p.num_chunks + chunk) * k;
             for (uint32_t i = lane; i < k; i += 32) {
                 uint64_t o = kNone;
