@@ -10,7 +10,7 @@ from np_sims import _lib
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 16_000_000
 for w in (1, 2, 4, 8, 10, 16, 32):
     H = torch.randint(-2**63, 2**63 - 1, (rows, w), dtype=torch.int64, device="cuda")
-    for nq in (1, 2, 4):
+    for nq in (1, 2, 4, 8, 15):
         q = torch.randint(-2**63, 2**63 - 1, (nq, w), dtype=torch.int64, device="cuda")
         for _ in range(3):
             np_sims.hamming_top_n(H, q, 10)
