@@ -149,3 +149,20 @@ def test_choose_sharding_and_query_bounds():
         for g in (1, 2, 3, 8):
             b = query_bounds(q, g)
             assert b[0] == 0 and b[-1] == q and all(b[i] <= b[i + 1] for i in range(g))
+
+
+def test_recall_harness_helpers_cpu():
+    """benchmark/recall.py pieces that need no GPU: synthetic data shape / norms, the split, recall@10."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "recall_harness", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmark", "recall.py"))
+    rec = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rec)
+    x = rec.synthetic_vectors(500, 32, 10, 1)
+    assert x.shape == (500, 32) and x.dtype == np.float32
+    assert np.allclose(np.linalg.norm(x, axis=1), 1.0, atol=1e-5)
+    q, ix = rec.test_train_split(x, 40, np.random.default_rng(0))
+    assert q.shape == (40, 32) and ix.shape == (460, 32)
+    ids = np.arange(20).reshape(2, 10)
+    gt = np.array([np.arange(10), np.arange(5, 15)])
+    assert rec.recall_at_10(ids, gt) == (1.0 + 0.0) / 2
