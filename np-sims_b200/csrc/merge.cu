@@ -122,14 +122,24 @@ __global__ void __launch_bounds__(256) merge_small_kernel(const uint64_t* __rest
     }
 }
 
-uint32_t merge_group_size(uint32_t k) {
+// Lists merged per CTA and pass.  As many as fit in shared memory when there are plenty of queries to fill
+// the GPU; with few queries (the single-query scan: 148 lists, 1 CTA per group) a CTA that ranks 4096 keys
+// against 127 other lists is the whole kernel (0.39 ms at k = 32), so the groups shrink to ~sqrt(lists):
+// more CTAs in the first pass, a short second one.
+uint32_t merge_group_size(uint32_t k, uint32_t Q, uint32_t lists) {
     uint32_t G = kMergeSmemKeys / (k ? k : 1);
-    return G < 2 ? 2 : G;
+    if (G < 2) G = 2;
+    if ((uint64_t)Q * ((lists + G - 1) / G) < 148u) {
+        uint32_t r = 2;
+        while (r * r < lists) ++r;
+        if (r < G) G = r;
+    }
+    return G;
 }
 
 size_t merge_scratch_keys(uint32_t Q, uint32_t lists, uint32_t k) {
     // ping-pong buffer for intermediate passes: the first pass shrinks lists by G
-    const uint32_t G = merge_group_size(k);
+    const uint32_t G = merge_group_size(k, Q, lists);
     if (lists <= G) return 0;
     const uint32_t l1 = (lists + G - 1) / G;
     const uint32_t l2 = (l1 + G - 1) / G;
@@ -147,7 +157,7 @@ cudaError_t launch_merge(const uint64_t* keys, uint32_t Q, uint32_t lists, uint3
         count_launch();
         return cudaGetLastError();
     }
-    const uint32_t G = merge_group_size(k);
+    const uint32_t G = merge_group_size(k, Q, lists);
     const uint32_t gx = gate ? (Q < 592u ? Q : 592u) : Q;   // gated: small grid-stride grid
     const size_t smem = (size_t)(G < lists ? G : lists) * k * sizeof(uint64_t);
     cudaError_t e = cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
