@@ -404,6 +404,10 @@ def run_b200(args, wl):
             "traffic": ncu_traffic("mma_scan_kernel") if (world == 1 and wl is WORKLOADS["c2"]) else None,
             "peak_source": "4 x measured bf16 burst (MEASURED_PEAKS.json): mxf4 : bf16 = 9 : 2.25 PFLOP/s nominal; "
                            "scripts/ubench/umma_mxf4_probe measured 16359 MAC/clk/SM issue rate in-kernel",
+            "frac_of_measured_mxf4_issue_rate": ach / (16359 * 2 * 148 * sm_mhz * 1e6 / 1e12),
+            "measured_mxf4_issue_rate_note": "scripts/ubench/umma_mxf4_probe.cu: 16359 MAC/clk/SM back-to-back = "
+                                             f"{16359 * 2 * 148 * sm_mhz * 1e6 / 1e12:.0f} TFLOP/s at {sm_mhz:.0f} MHz — a stricter "
+                                             "denominator than 4 x the measured bf16 GEMM rate",
             "ms_per_launch": ph_ms[dom], "share_of_step": ph_ms[dom] / step_ms,
             "algorithmic": {"rows": rows_dom, "queries": nq_local, "bits": wl["bits"], "flop": flop_dom},
             "phases": [{"tiles": t, "scan_ms": m} for t, m in zip(tiles, ph_ms)],
