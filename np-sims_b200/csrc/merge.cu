@@ -139,6 +139,7 @@ uint32_t merge_group_size(uint32_t k, uint32_t Q, uint32_t lists) {
 
 size_t merge_scratch_keys(uint32_t Q, uint32_t lists, uint32_t k) {
     // ping-pong buffer for intermediate passes: the first pass shrinks lists by G
+    if (k <= kSmallMergeK && (uint64_t)lists * k <= kSmallMergeKeys) return 0;   // merge_small_kernel: one pass
     const uint32_t G = merge_group_size(k, Q, lists);
     if (lists <= G) return 0;
     const uint32_t l1 = (lists + G - 1) / G;

@@ -73,12 +73,19 @@ def hash_stats():
     the device.  Synchronises the stream; the hashing call itself never does."""
     st = dict(last_hash_stats)
     if st["path"] == "tc-split+fixup" and _last_hash_ws is not None:
-        import ctypes
-        ws, n, b = _last_hash_ws
-        fixed, cap = ctypes.c_uint32(0), ctypes.c_uint32(0)
-        _lib.call("nps_project_sign_pack_stats", ptr(ws), n, b, stream_ptr(), ctypes.byref(fixed), ctypes.byref(cap))
-        st.update(recomputed=int(fixed.value), overflowed=fixed.value > cap.value)
+        counter, cap = _last_hash_ws
+        fixed = int(counter.cpu().numpy().view(np.uint32)[0])
+        st.update(recomputed=fixed, overflowed=fixed > cap)
     return st
+
+
+def _remember_hash_workspace(ws, ws_bytes, n):
+    """Keep what `hash_stats` needs from the K1T workspace (layout, project_tc.cu: |x| norms, then the
+    fix-up counter, then the list): a 4-byte copy of the counter and the list capacity — not the
+    workspace itself, which is 10 GB for the C3 table."""
+    global _last_hash_ws
+    off = (4 * n + 255) // 256 * 256
+    _last_hash_ws = (ws[off:off + 4].clone(), (ws_bytes - off - 256) // 8)
 
 
 def _projections_split(projections, P64):
@@ -131,7 +138,7 @@ def hash_vectors(vectors, projections, return_dots=False, exact_only=False, tf32
             ws = t.empty(ws_bytes, dtype=t.uint8, device=P.device)
             _lib.call("nps_project_sign_pack", ptr(X), n, d, ptr(split), ptr(P), b, 1e-30 if tf32_raw else norm_max,
                       ptr(out), ptr(ws), ws_bytes, stream_ptr())
-            _last_hash_ws = (ws, n, b)
+            _remember_hash_workspace(ws, ws_bytes, n)
             last_hash_stats.update(path="tc-split+fixup", pairs=n * b, recomputed=None)
             return out
         dots = t.empty((n, b), dtype=t.float64, device=P.device) if return_dots else None

@@ -149,10 +149,15 @@ def hamming_rerank(hashes, query, candidates, n=10, return_distances=False):
 _last_ws = None
 
 
+_KEEP_WHOLE_BYTES = 64 << 20
+
+
 def _remember_workspace(ws):
-    """Keep the last top-n workspace alive so `last_overflow_count` can read its overflow counter."""
+    """Keep what `last_overflow_count` needs: the overflow counter is the first word of the workspace.
+    Small workspaces (single queries) are kept whole — no extra launch; of large ones (a C4 batch needs
+    2 GB) only a 4-byte copy survives the call."""
     global _last_ws
-    _last_ws = ws
+    _last_ws = ws if ws.numel() <= _KEEP_WHOLE_BYTES else ws[:4].clone()
 
 
 def last_overflow_count() -> int:
