@@ -342,7 +342,8 @@ def test_torch_tensor_inputs_stay_on_device(nps):
 
 # ------------------------------------------------------------------------------ K1T tensor-core hashing
 @pytest.mark.parametrize("n,dims,bits", [(1, 300, 640), (127, 300, 640), (1019, 300, 640), (5000, 768, 1024),
-                                         (3001, 100, 128), (2000, 52, 64), (4096, 300, 2560)])
+                                         (3001, 100, 128), (2000, 52, 64), (4096, 300, 2560),
+                                         (200, 8, 64), (333, 36, 128)])       # TMA boxes wider than the matrix
 def test_tensor_core_hash_equals_float64_oracle(nps, n, dims, bits):
     """K1T (tcgen05 GEMM on two-term splits of both operands + float64 fix-up) must give the oracle's
     float64 signatures with either operand encoding — BF16 x 2 (default) and TF32 x 2; the bare
