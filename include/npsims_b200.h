@@ -51,7 +51,11 @@ int nps_device_count(void);
 /* Measurement aids (bench.py): with profiling on, every nps_hamming_top_n* call brackets its
  * scan (K2) and merge (K3) launches with CUDA events on the caller's stream;
  * nps_profile_last() waits for them and returns the two device durations in milliseconds.
- * nps_last_scan_plan() reports how the last call was tiled. Not thread-safe; off by default. */
+ * nps_last_scan_plan() reports how the last call was tiled.  Off by default.
+ * Threading: the profiling switch, the forced kernel families (nps_set_scan_path,
+ * nps_set_hash_path) and every nps_last_* diagnostic are PER HOST THREAD (thread_local): they
+ * describe and affect only calls made by the same thread.  All compute entry points are
+ * re-entrant across host threads as long as each call uses its own stream / workspace / outputs. */
 typedef struct nps_scan_plan {
     uint32_t tile_rows, tile_bytes, stages, q_tile, num_qtiles, chunk_rows, num_chunks, cap,
         smem_bytes, grid, specialised, rows_per_thread;
@@ -59,9 +63,12 @@ typedef struct nps_scan_plan {
 int nps_profile_enable(int on);
 int nps_profile_last(float *scan_ms, float *merge_ms);
 int nps_last_scan_plan(nps_scan_plan_t *out);
-/* Kernel family of the top-n scan.  AUTO: batches of >= 64 queries over >= 4096 rows run on
- * the tensor cores (tcgen05 E4M3 +-1 GEMM, exact), everything else on the XOR+POPC streaming
- * scan.  Forcing a family is for tests and measurements; results are identical. */
+/* Kernel family of the top-n scan.  AUTO: batches of >= 64 queries over >= 4096 rows, and
+ * batches of >= 16 queries once rows * queries * words >= 1e9, run on the tensor cores
+ * (tcgen05 kind::mxf4 block-scaled GEMM over E2M1 +-1 operands with unit scales, FP32
+ * accumulation in TMEM: exact integers, csrc/mma_scan.cu); everything else on the XOR+POPC
+ * streaming scan (csrc/scan.cuh).  Forcing a family is for tests and measurements; results are
+ * identical. */
 #define NPS_SCAN_AUTO 0
 #define NPS_SCAN_POPC 1
 #define NPS_SCAN_MMA 2
@@ -112,6 +119,30 @@ int nps_index_query_top_n(nps_index_t *index, const uint64_t *host_queries, uint
 /* Full distances of one query against the resident table: host_out[num_hashes]. */
 int nps_index_hamming(nps_index_t *index, const uint64_t *host_query, uint64_t *host_out);
 
+/* The reference's own calling pattern — one query per call, many host threads over a shared
+ * read-only table (benchmark/glove.py:183-199; the GIL is released at ufunc.c:456-457) — over a table
+ * that is ALREADY resident in HBM (d_hashes [num_hashes, words], 16-byte aligned, owned by the caller
+ * and alive as long as the searcher).  Thread-safe: every calling thread takes its own slot (stream,
+ * pinned staging, workspace); a call is one CUDA-graph launch (H2D copy, [hash kernel,] K2R prefix +
+ * scan/replay kernels, D2H copy) and one stream synchronisation.  Results are bit-identical to the
+ * reference queue (slot order, NPS_NONE padding).  words <= 63.
+ *   nps_searcher_top_k        : gufuncs hamming_top_10 (k = 10) / hamming_top_cand (k = 1000),
+ *                               ufunc.c:444-551; host_query[words] -> host_rows[k]
+ *   nps_searcher_query_vector : lsh.query (lsh.py:70-74): host_vector[dims] float32 / float64 ->
+ *                               float64 projection + sign + pack (lsh.py:31-33, d_projections
+ *                               [num_projections, dims] float64 in HBM) -> the same search */
+typedef struct nps_searcher nps_searcher_t;
+int nps_searcher_create(const uint64_t *d_hashes, uint64_t num_hashes, uint32_t words, int device,
+                        nps_searcher_t **out_searcher);
+void nps_searcher_destroy(nps_searcher_t *searcher);
+int nps_searcher_top_k(nps_searcher_t *searcher, const uint64_t *host_query, uint32_t k, uint64_t *host_rows);
+int nps_searcher_query_vector(nps_searcher_t *searcher, const void *host_vector, int vector_is_f32,
+                              uint32_t dims, const double *d_projections, uint32_t num_projections,
+                              uint32_t k, uint64_t *host_rows);
+/* diagnostics: calls served, calls that took the dense fallback, slots created */
+int nps_searcher_stats(nps_searcher_t *searcher, unsigned long long *calls, unsigned long long *fallbacks,
+                       uint32_t *slots);
+
 /* ------------------------------------------------------------------ B. device level ----- */
 
 /* K5 — gufunc `hamming` (ufunc.c:74-106), batched: d_out[num_queries, num_hashes] of
@@ -142,17 +173,26 @@ int nps_hamming_top_n_keys(const uint64_t *d_hashes, uint64_t num_hashes, uint32
 /* K4 — merge `num_lists` candidate-key lists per query (layout [num_queries, num_lists, k] or,
  * with list_major != 0, [num_lists, num_queries, k] as an all-gather leaves them) into the
  * final [num_queries, k] ids/distances.  No reference equivalent (the reference is
- * single-process); equals running the search on the concatenated table. */
+ * single-process); equals running the search on the concatenated table.  Preconditions: every
+ * list ascending and NPS_NONE padded, keys unique ACROSS the lists of a query (true for shards
+ * of one table: the row id is part of the key) — a key present in two lists leaves output
+ * slots unwritten. */
 size_t nps_top_n_merge_workspace_bytes(uint32_t num_queries, uint32_t num_lists, uint32_t k);
 int nps_top_n_merge(const uint64_t *d_keys, uint32_t num_lists, uint32_t num_queries, uint32_t k,
                     int list_major, uint64_t *d_out_rows, uint64_t *d_out_dists, void *d_workspace,
                     size_t workspace_bytes, void *stream);
 
-/* Reference-exact order (NPS_ORDER_REFERENCE): K5 into the workspace, then the on-device
- * replay of the reference queue (ufunc.c:150-195).  d_out_rows [num_queries, k] in slot
- * order; d_out_scores (nullable) the slot distances. */
+/* Reference-exact order (NPS_ORDER_REFERENCE) — gufuncs `hamming_top_10` / `hamming_top_cand`
+ * (ufunc.c:444-551) with the queue of ufunc.c:108-195 reproduced bit for bit: d_out_rows
+ * [num_queries, k] in SLOT order, NPS_NONE where a slot was never filled; d_out_scores (nullable)
+ * the slot distances.  K2R (csrc/ref_scan.cuh): a prefix kernel bounds the queue's worst, a
+ * streaming scan at HBM speed keeps the rows that can ever enter the queue, the last CTA replays
+ * them in row order — two launches (one for tables <= 32768 rows).  Signatures wider than 63 words,
+ * unaligned tables and (gated on a device flag, no host round trip) adversarial row orders take
+ * K5 + the dense replay (csrc/replay.cu).  d_workspace: 256-byte aligned,
+ * nps_hamming_top_n_reference_workspace_bytes(num_hashes, words, num_queries, k) bytes. */
 size_t nps_hamming_top_n_reference_workspace_bytes(uint64_t num_hashes, uint32_t words,
-                                                   uint32_t num_queries);
+                                                   uint32_t num_queries, uint32_t k);
 int nps_hamming_top_n_reference(const uint64_t *d_hashes, uint64_t num_hashes, uint32_t words,
                                 const uint64_t *d_queries, uint32_t num_queries, uint32_t k,
                                 uint64_t *d_out_rows, uint64_t *d_out_scores, void *d_workspace,

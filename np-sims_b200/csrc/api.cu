@@ -12,6 +12,7 @@
 #include "merge.cuh"
 #include "mma_scan.cuh"
 #include "project.cuh"
+#include "ref_scan.cuh"
 #include "replay.cuh"
 #include "rerank.cuh"
 #include "scan.cuh"
@@ -21,7 +22,7 @@ namespace nps {
 unsigned long long g_launch_count = 0;
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, ...) {
+int fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -64,21 +65,53 @@ static int device_info(DeviceInfo* out) {
 // ---------------------------------------------------------------------------- profiling aid
 // When enabled (bench.py's roofline pass only), run_top_n brackets K2 and K3 with CUDA events
 // on the launching stream so the dominant kernel can be timed per launch, on the device.
-static bool g_profile = false;
-static int g_scan_path = NPS_SCAN_AUTO;     // nps_set_scan_path
-static int g_last_path = NPS_SCAN_POPC;     // which kernel family the last top-n call used
-static MmaPlan g_last_mma_plan = {};
-static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
-static cudaEvent_t g_phase_ev[2 * kMmaMaxPhases] = {};   // tensor-core path: one pair per phase
-static ScanPlanInfo g_last_plan = {};
+// All of this is PER HOST THREAD (thread_local): the measurement switches, the forced kernel
+// family and the "last plan" diagnostics of one thread never affect a call made by another, so the
+// library can be driven from many host threads (the reference's ThreadPoolExecutor pattern).  The
+// profiling events belong to the device that was current when they were created and are re-created
+// when the thread moves to another device.
+static thread_local bool g_profile = false;
+static thread_local int g_scan_path = NPS_SCAN_AUTO;     // nps_set_scan_path
+static thread_local int g_last_path = NPS_SCAN_POPC;     // which kernel family the last top-n call used
+static thread_local MmaPlan g_last_mma_plan = {};
+static thread_local cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
+static thread_local cudaEvent_t g_phase_ev[2 * kMmaMaxPhases] = {};   // tensor-core path: one pair per phase
+static thread_local int g_ev_device = -1;
+static thread_local ScanPlanInfo g_last_plan = {};
 
 static int profile_events() {
+    int dev = 0;
+    NPS_CUDA(cudaGetDevice(&dev));
+    if (g_ev_device != dev) {
+        for (auto& e : g_ev)
+            if (e) {
+                cudaEventDestroy(e);
+                e = nullptr;
+            }
+        for (auto& e : g_phase_ev)
+            if (e) {
+                cudaEventDestroy(e);
+                e = nullptr;
+            }
+        g_ev_device = dev;
+    }
     for (auto& e : g_ev)
         if (!e) NPS_CUDA(cudaEventCreate(&e));
     for (auto& e : g_phase_ev)
         if (!e) NPS_CUDA(cudaEventCreate(&e));
     return NPS_OK;
 }
+
+struct DeviceGuard {   // host-level entry points leave the caller's current device as it was
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
 
 // ---------------------------------------------------------------------------- scan planning
 struct ScanPlan {
@@ -489,11 +522,30 @@ int nps_top_n_merge(const uint64_t* d_keys, uint32_t num_lists, uint32_t num_que
     return NPS_OK;
 }
 
-size_t nps_hamming_top_n_reference_workspace_bytes(uint64_t num_hashes, uint32_t words, uint32_t num_queries) {
-    const size_t elt = (64ull * words > 65535ull) ? 4 : 2;
-    // every query's distance row starts 16-byte aligned
-    const size_t row = (num_hashes * elt + 15) & ~(size_t)15;
-    return align256(row * num_queries);
+// Workspace of the reference-order search: [header | nq x K2R blocks | nq x dense distance rows (fallback)]
+struct RefWorkspace {
+    RefPlan plan;
+    size_t fast_bytes, row_bytes, total;
+    int elt;
+};
+static RefWorkspace ref_workspace(uint64_t N, uint32_t W, uint32_t nq, uint32_t k, const DeviceInfo& dev) {
+    RefWorkspace w;
+    w.plan = ref_plan(N, W, k, dev.sm_count, dev.smem_optin);
+    w.elt = (64ull * W > 65535ull) ? 4 : 2;
+    w.row_bytes = ((size_t)N * w.elt + 15) & ~(size_t)15;      // every query's distance row starts 16-byte aligned
+    w.fast_bytes = w.plan.applicable ? align256(kRefHeaderBytes + (size_t)nq * w.plan.ws_stride) : 0;
+    w.total = w.fast_bytes + align256(w.row_bytes * nq);
+    return w;
+}
+
+size_t nps_hamming_top_n_reference_workspace_bytes(uint64_t num_hashes, uint32_t words, uint32_t num_queries, uint32_t k) {
+    DeviceInfo dev;
+    if (device_info(&dev) != NPS_OK) {
+        dev.sm_count = 148;
+        dev.smem_optin = 232448;
+    }
+    if (words == 0 || words > NPS_MAX_WORDS || k == 0 || k > NPS_MAX_K) return 0;
+    return ref_workspace(num_hashes, words, num_queries ? num_queries : 1, k, dev).total;
 }
 
 int nps_hamming_top_n_reference(const uint64_t* d_hashes, uint64_t num_hashes, uint32_t words,
@@ -503,19 +555,29 @@ int nps_hamming_top_n_reference(const uint64_t* d_hashes, uint64_t num_hashes, u
     if (k == 0 || k > NPS_MAX_K) return fail(NPS_EINVAL, "k=%u outside [1, %u]", k, NPS_MAX_K);
     if (num_queries == 0) return NPS_OK;
     if (!d_queries || !d_out_rows || (!d_hashes && num_hashes)) return fail(NPS_EINVAL, "null pointer");
-    const int elt = (64ull * words > 65535ull) ? 4 : 2;
-    const size_t need = nps_hamming_top_n_reference_workspace_bytes(num_hashes, words, num_queries);
-    if (num_hashes && (!d_workspace || workspace_bytes < need))
-        return fail(NPS_EWORKSPACE, "workspace %zu bytes < required %zu", workspace_bytes, need);
     DeviceInfo dev;
     int rc = device_info(&dev);
     if (rc) return rc;
+    const RefWorkspace w = ref_workspace(num_hashes, words, num_queries, k, dev);
+    if (!d_workspace || workspace_bytes < w.total)
+        return fail(NPS_EWORKSPACE, "workspace %zu bytes < required %zu", workspace_bytes, w.total);
+    if (reinterpret_cast<uintptr_t>(d_workspace) & 255u) return fail(NPS_EINVAL, "workspace must be 256-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    // The replay kernel indexes query q's distances at q * N elements, so rows must be packed;
-    // 16-byte alignment of each row then holds only when N*elt % 16 == 0 — the kernel checks
-    // alignment per row and falls back to scalar loads otherwise.
-    NPS_CUDA(launch_hamming_dist(d_hashes, num_hashes, words, d_queries, num_queries, d_workspace, elt, dev.sm_count, s));
-    NPS_CUDA(launch_replay_queue(d_workspace, elt, num_hashes, num_queries, k, d_out_rows, d_out_scores, s));
+    void* dense = reinterpret_cast<uint8_t*>(d_workspace) + w.fast_bytes;
+    const uint32_t* gate = nullptr;
+    const bool fast = w.plan.applicable && (reinterpret_cast<uintptr_t>(d_hashes) & 15u) == 0;
+    if (fast) {
+        // K2R: prefix kernel + streaming superset scan + replay by the last CTA (ref_scan.cuh)
+        NPS_CUDA(run_ref_top_n(w.plan, d_hashes, num_hashes, words, d_queries, num_queries, k, d_out_rows, d_out_scores,
+                               d_workspace, s));
+        gate = reinterpret_cast<const uint32_t*>(d_workspace);   // fallback below runs only if a segment overflowed
+        if (num_hashes <= kRefSmallRows) return NPS_OK;           // all prefix: nothing can overflow
+    }
+    // K5 + dense replay: the only path for signatures wider than kRefMaxWords words, the gated
+    // fallback otherwise.  The replay kernel indexes query q's distances at q * N elements, so rows
+    // are packed; it checks alignment per row and falls back to scalar loads.
+    NPS_CUDA(launch_hamming_dist(d_hashes, num_hashes, words, d_queries, num_queries, dense, w.elt, dev.sm_count, s, gate));
+    NPS_CUDA(launch_replay_queue(dense, w.elt, num_hashes, num_queries, k, d_out_rows, d_out_scores, s, gate));
     return NPS_OK;
 }
 
@@ -563,7 +625,7 @@ size_t nps_project_sign_pack_workspace_bytes(uint64_t num_vectors, uint32_t num_
 
 size_t nps_project_split_bytes(uint32_t num_projections, uint32_t dims) { return project_split_bytes(num_projections, dims); }
 
-static int g_hash_path = NPS_HASH_AUTO;
+static thread_local int g_hash_path = NPS_HASH_AUTO;
 int nps_set_hash_path(int path) {
     if (path != NPS_HASH_AUTO && path != NPS_HASH_TF32 && path != NPS_HASH_BF16) return fail(NPS_EINVAL, "bad hash path %d", path);
     g_hash_path = path;
@@ -663,7 +725,7 @@ int nps_index_create(const uint64_t* host_hashes, uint64_t num_hashes, uint32_t 
     *out_index = nullptr;
     if (words == 0 || words > NPS_MAX_WORDS) return fail(NPS_EINVAL, "words=%u outside [1, %u]", words, NPS_MAX_WORDS);
     if (!host_hashes && num_hashes) return fail(NPS_EINVAL, "host_hashes is null");
-    NPS_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
     nps_index* ix = new (std::nothrow) nps_index();
     if (!ix) return fail(NPS_EINVAL, "out of host memory");
     ix->device = device;
@@ -685,7 +747,7 @@ int nps_index_create(const uint64_t* host_hashes, uint64_t num_hashes, uint32_t 
 
 void nps_index_destroy(nps_index_t* ix) {
     if (!ix) return;
-    cudaSetDevice(ix->device);
+    DeviceGuard guard(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     if (ix->d_hashes) cudaFree(ix->d_hashes);
     if (ix->d_ws) cudaFree(ix->d_ws);
@@ -703,11 +765,11 @@ int nps_index_query_top_n(nps_index_t* ix, const uint64_t* host_queries, uint32_
     if (!host_queries || !host_rows) return fail(NPS_EINVAL, "null pointer");
     if (k == 0 || k > NPS_MAX_K) return fail(NPS_EINVAL, "k=%u outside [1, %u]", k, NPS_MAX_K);
     if (order != NPS_ORDER_CANONICAL && order != NPS_ORDER_REFERENCE) return fail(NPS_EINVAL, "bad order %d", order);
-    NPS_CUDA(cudaSetDevice(ix->device));
+    DeviceGuard guard(ix->device);
     // the reference-order path materialises [batch, N] distances: bound the batch
     uint32_t batch = num_queries;
     if (order == NPS_ORDER_REFERENCE) {
-        const size_t per_q = nps_hamming_top_n_reference_workspace_bytes(ix->num_hashes, ix->words, 1);
+        const size_t per_q = nps_hamming_top_n_reference_workspace_bytes(ix->num_hashes, ix->words, 1, k);
         const size_t budget = (size_t)1 << 30;
         const size_t fit = per_q ? budget / per_q : num_queries;
         batch = (uint32_t)(fit < 1 ? 1 : (fit < num_queries ? fit : num_queries));
@@ -716,7 +778,7 @@ int nps_index_query_top_n(nps_index_t* ix, const uint64_t* host_queries, uint32_
         const uint32_t nq = (num_queries - q0) < batch ? (num_queries - q0) : batch;
         const size_t ws = order == NPS_ORDER_CANONICAL
                               ? nps_hamming_top_n_workspace_bytes(ix->num_hashes, ix->words, nq, k)
-                              : nps_hamming_top_n_reference_workspace_bytes(ix->num_hashes, ix->words, nq);
+                              : nps_hamming_top_n_reference_workspace_bytes(ix->num_hashes, ix->words, nq, k);
         if (order == NPS_ORDER_CANONICAL && ws == 0) return NPS_EINVAL;   // message set by the planner
         int rc = index_reserve(ix, ws, (size_t)nq * ix->words, (size_t)nq * k);
         if (rc) return rc;
@@ -743,7 +805,7 @@ int nps_index_hamming(nps_index_t* ix, const uint64_t* host_query, uint64_t* hos
     if (!ix) return fail(NPS_EINVAL, "index is null");
     if (!host_query || (!host_out && ix->num_hashes)) return fail(NPS_EINVAL, "null pointer");
     if (ix->num_hashes == 0) return NPS_OK;
-    NPS_CUDA(cudaSetDevice(ix->device));
+    DeviceGuard guard(ix->device);
     int rc = index_reserve(ix, (size_t)ix->num_hashes * 8, ix->words, 0);
     if (rc) return rc;
     NPS_CUDA(cudaMemcpyAsync(ix->d_q, host_query, (size_t)ix->words * 8, cudaMemcpyHostToDevice, ix->stream));

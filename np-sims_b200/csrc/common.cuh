@@ -89,6 +89,11 @@ __device__ __forceinline__ void consumer_bar() {
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
 }
 
+// named barrier with run-time id / thread count (thread count a multiple of 32)
+__device__ __forceinline__ void named_bar_sync_rt(uint32_t id, uint32_t threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // ---- shared-memory accessors ----------------------------------------------------------------
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
@@ -108,6 +113,9 @@ __device__ __forceinline__ uint32_t lds32_volatile(const uint32_t* p) {
 __device__ __forceinline__ void sts32_volatile(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
+
+// sets the thread-local message returned by nps_last_error() and returns `code` (api.cu)
+int fail(int code, const char* fmt, ...);
 
 // cumulative count of kernel launches issued by this library (bench.py's gpu_launches)
 extern unsigned long long g_launch_count;

@@ -18,8 +18,10 @@ template <typename OutT>
 __global__ void __launch_bounds__(kDistThreads) hamming_dist_kernel(const uint64_t* __restrict__ H,
                                                                     unsigned long long N, uint32_t W,
                                                                     const uint64_t* __restrict__ Q, uint32_t nq,
-                                                                    OutT* __restrict__ out, uint32_t tile_rows) {
+                                                                    OutT* __restrict__ out, uint32_t tile_rows,
+                                                                    const uint32_t* __restrict__ gate) {
     extern __shared__ __align__(16) uint64_t sm[];
+    if (gate != nullptr && *gate == 0u) return;   // gated fallback launch, nothing to redo
     const uint32_t stride = W | 1u;
     uint64_t* rows_s = sm;                                // [tile_rows][stride]
     uint64_t* q_s = sm + (size_t)tile_rows * stride;      // [kDistQBatch][W]
@@ -63,7 +65,7 @@ uint32_t hamming_tile_rows(uint32_t W) {
 
 template <typename OutT>
 static cudaError_t launch_dist_t(const uint64_t* H, unsigned long long N, uint32_t W, const uint64_t* Q, uint32_t nq,
-                                 void* out, int sm_count, cudaStream_t stream) {
+                                 void* out, int sm_count, cudaStream_t stream, const uint32_t* gate) {
     const uint32_t tile_rows = hamming_tile_rows(W);
     const size_t smem = ((size_t)tile_rows * (W | 1u) + (size_t)kDistQBatch * W) * 8;
     auto kern = hamming_dist_kernel<OutT>;
@@ -71,18 +73,18 @@ static cudaError_t launch_dist_t(const uint64_t* H, unsigned long long N, uint32
     if (e != cudaSuccess) return e;
     unsigned long long tiles = (N + tile_rows - 1) / tile_rows;
     unsigned long long grid = tiles < (unsigned long long)sm_count * 8 ? tiles : (unsigned long long)sm_count * 8;
-    kern<<<(unsigned)grid, kDistThreads, smem, stream>>>(H, N, W, Q, nq, (OutT*)out, tile_rows);
+    kern<<<(unsigned)grid, kDistThreads, smem, stream>>>(H, N, W, Q, nq, (OutT*)out, tile_rows, gate);
     count_launch();
     return cudaGetLastError();
 }
 
 cudaError_t launch_hamming_dist(const uint64_t* H, unsigned long long N, uint32_t W, const uint64_t* Q, uint32_t nq,
-                                void* out, int out_bytes, int sm_count, cudaStream_t stream) {
+                                void* out, int out_bytes, int sm_count, cudaStream_t stream, const uint32_t* gate) {
     if (N == 0 || nq == 0) return cudaSuccess;
     switch (out_bytes) {
-        case 2: return launch_dist_t<uint16_t>(H, N, W, Q, nq, out, sm_count, stream);
-        case 4: return launch_dist_t<uint32_t>(H, N, W, Q, nq, out, sm_count, stream);
-        case 8: return launch_dist_t<uint64_t>(H, N, W, Q, nq, out, sm_count, stream);
+        case 2: return launch_dist_t<uint16_t>(H, N, W, Q, nq, out, sm_count, stream, gate);
+        case 4: return launch_dist_t<uint32_t>(H, N, W, Q, nq, out, sm_count, stream, gate);
+        case 8: return launch_dist_t<uint64_t>(H, N, W, Q, nq, out, sm_count, stream, gate);
         default: return cudaErrorInvalidValue;
     }
 }

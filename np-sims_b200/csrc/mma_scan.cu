@@ -1,6 +1,7 @@
 // mma_scan.cu — K2T kernels: tensor-core batched Hamming scan + candidate select.
 // See mma_scan.cuh for the design.  Replaces, for query batches, the scan bodies of
-// np_sims/ufunc.c:207-441 (XOR + popcount + queue insert) with an exact +-1 E4M3 GEMM.
+// np_sims/ufunc.c:207-441 (XOR + popcount + queue insert) with an exact +-1 GEMM on E2M1 operands
+// (tcgen05 kind::mxf4, unit block scales).
 #include <cstdio>
 #include <cstdlib>
 

@@ -30,7 +30,9 @@ template <typename DistT>
 __global__ void __launch_bounds__(kReplayThreads, 1) replay_queue_kernel(const DistT* __restrict__ dist,
                                                                          unsigned long long N, uint32_t k,
                                                                          uint64_t* __restrict__ out_rows,
-                                                                         uint64_t* __restrict__ out_scores) {
+                                                                         uint64_t* __restrict__ out_scores,
+                                                                         const uint32_t* __restrict__ gate) {
+    if (gate != nullptr && *gate == 0u) return;   // gated fallback launch (ref_scan.cu), nothing to redo
     constexpr int EPV = 16 / sizeof(DistT);                 // elements per vector
     constexpr int EPT = EPV * kReplayVecs;                  // elements per thread per tile
     constexpr uint32_t TILE = kReplayThreads * EPT;
@@ -197,21 +199,21 @@ __global__ void __launch_bounds__(kReplayThreads, 1) replay_queue_kernel(const D
 
 template <typename DistT>
 static cudaError_t launch_t(const void* dist, unsigned long long N, uint32_t nq, uint32_t k, uint64_t* out_rows,
-                            uint64_t* out_scores, cudaStream_t stream) {
+                            uint64_t* out_scores, cudaStream_t stream, const uint32_t* gate) {
     const size_t smem = ((k * 4 + 15) & ~15u) + (size_t)k * 8;
     auto kern = replay_queue_kernel<DistT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<nq, kReplayThreads, smem, stream>>>((const DistT*)dist, N, k, out_rows, out_scores);
+    kern<<<nq, kReplayThreads, smem, stream>>>((const DistT*)dist, N, k, out_rows, out_scores, gate);
     count_launch();
     return cudaGetLastError();
 }
 
 cudaError_t launch_replay_queue(const void* dist, int dist_bytes, unsigned long long N, uint32_t nq, uint32_t k,
-                                uint64_t* out_rows, uint64_t* out_scores, cudaStream_t stream) {
+                                uint64_t* out_rows, uint64_t* out_scores, cudaStream_t stream, const uint32_t* gate) {
     if (nq == 0 || k == 0) return cudaSuccess;
-    if (dist_bytes == 2) return launch_t<uint16_t>(dist, N, nq, k, out_rows, out_scores, stream);
-    if (dist_bytes == 4) return launch_t<uint32_t>(dist, N, nq, k, out_rows, out_scores, stream);
+    if (dist_bytes == 2) return launch_t<uint16_t>(dist, N, nq, k, out_rows, out_scores, stream, gate);
+    if (dist_bytes == 4) return launch_t<uint32_t>(dist, N, nq, k, out_rows, out_scores, stream, gate);
     return cudaErrorInvalidValue;
 }
 

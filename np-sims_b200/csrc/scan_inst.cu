@@ -5,6 +5,7 @@
 #define NPS_SCAN_GENERIC 1
 #endif
 #include "scan.cuh"
+#include "ref_scan.cuh"
 
 namespace nps {
 
@@ -19,7 +20,18 @@ static cudaError_t launch_scan_w(const ScanParams& p, int grid, size_t smem, cud
     return cudaGetLastError();
 }
 
-#define NPS_DECL_GROUP(g) ScanLaunchFn scan_launcher_group##g(int words);
+template <int W>
+static cudaError_t launch_ref_scan_w(const RefParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
+    constexpr int R = rows_per_thread(W);
+    auto kern = ref_scan_kernel<W, R>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kScanThreads, smem, stream>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+#define NPS_DECL_GROUP(g) ScanLaunchFn scan_launcher_group##g(int words); RefLaunchFn ref_launcher_group##g(int words);
 NPS_DECL_GROUP(0) NPS_DECL_GROUP(1) NPS_DECL_GROUP(2) NPS_DECL_GROUP(3)
 
 #if NPS_WGROUP < 4
@@ -32,7 +44,16 @@ NPS_DECL_GROUP(0) NPS_DECL_GROUP(1) NPS_DECL_GROUP(2) NPS_DECL_GROUP(3)
             default: return nullptr;                                       \
         }                                                                  \
     }
-#define NPS_DEFINE_GROUP(g) NPS_DEFINE_GROUP_(g)
+#define NPS_RCASE(w) case (NPS_WGROUP * 8 + w): return launch_ref_scan_w<NPS_WGROUP * 8 + w>;
+#define NPS_DEFINE_RGROUP_(g)                                              \
+    RefLaunchFn ref_launcher_group##g(int words) {                         \
+        switch (words) {                                                   \
+            NPS_RCASE(1) NPS_RCASE(2) NPS_RCASE(3) NPS_RCASE(4)            \
+            NPS_RCASE(5) NPS_RCASE(6) NPS_RCASE(7) NPS_RCASE(8)            \
+            default: return nullptr;                                       \
+        }                                                                  \
+    }
+#define NPS_DEFINE_GROUP(g) NPS_DEFINE_GROUP_(g) NPS_DEFINE_RGROUP_(g)
 NPS_DEFINE_GROUP(NPS_WGROUP)
 #else
 ScanLaunchFn scan_launcher_for_width(int words) {
@@ -43,6 +64,23 @@ ScanLaunchFn scan_launcher_for_width(int words) {
         case 2: return scan_launcher_group2(words);
         default: return scan_launcher_group3(words);
     }
+}
+RefLaunchFn ref_launcher_for_width(int words) {
+    if (words < 1 || words > 32) return nullptr;
+    switch ((words - 1) / 8) {
+        case 0: return ref_launcher_group0(words);
+        case 1: return ref_launcher_group1(words);
+        case 2: return ref_launcher_group2(words);
+        default: return ref_launcher_group3(words);
+    }
+}
+cudaError_t launch_ref_scan_generic(const RefParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
+    cudaError_t e =
+        cudaFuncSetAttribute(ref_scan_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ref_scan_generic_kernel<<<grid, kScanThreads, smem, stream>>>(p);
+    count_launch();
+    return cudaGetLastError();
 }
 cudaError_t launch_scan_generic(const ScanParams& p, int grid, size_t smem, cudaStream_t stream) {
     cudaError_t e =

@@ -1,6 +1,9 @@
 """Device-buffer plumbing: torch tensors carry HBM allocations and streams, nothing more."""
 from __future__ import annotations
 
+import ctypes
+import threading
+
 import numpy as np
 
 from . import _lib
@@ -41,24 +44,94 @@ class DeviceArray(np.ndarray):
 
     _nps_dev = None
     _nps_dev32 = None
+    _nps_searcher = None
 
     def __array_finalize__(self, obj):
         self._nps_dev = None
         self._nps_dev32 = None
+        self._nps_searcher = None
 
     def __reduce__(self):  # pickle / np.save as a plain array
         return np.asarray(self).view(np.ndarray).__reduce__()
 
 
 def attach(arr: np.ndarray, dev) -> "DeviceArray":
+    """`arr` as a DeviceArray that remembers its HBM copy `dev`.  While a device copy is attached the
+    array is read-only: an in-place write would silently leave a stale copy on the GPU (call
+    `forget_device(arr)` to drop the copy and write again)."""
     out = np.asarray(arr).view(DeviceArray)
     out._nps_dev = dev
+    if dev is not None:
+        _freeze(out)
     return out
+
+
+def _freeze(arr) -> None:
+    try:
+        arr.flags.writeable = False
+    except ValueError:
+        pass
 
 
 def forget_device(arr) -> None:
     if isinstance(arr, DeviceArray):
         arr._nps_dev = None
+        arr._nps_dev32 = None
+        arr._nps_searcher = None
+        try:
+            arr.flags.writeable = True
+        except ValueError:      # a view of a read-only base
+            pass
+
+
+class Searcher:
+    """Handle of the C-level single-query searcher (csrc/searcher.cu: per-thread slots, one CUDA graph per
+    call) over a table resident in HBM.  Keeps the table tensor alive."""
+
+    def __init__(self, table):
+        t = torch()
+        handle = ctypes.c_void_p()
+        with t.cuda.device(table.device):
+            _lib.check(_lib.raw("nps_searcher_create")(table.data_ptr(), table.shape[0], table.shape[1],
+                                                       table.device.index or 0, ctypes.byref(handle)))
+        self.handle = handle.value
+        self.table = table
+        self.words = int(table.shape[1])
+        self.proj = None          # (id(projections object), tensor, ptr, B, D) of the last lsh.query
+        self._destroy = _lib.raw("nps_searcher_destroy")
+
+    def stats(self):
+        calls, fallbacks, slots = ctypes.c_ulonglong(), ctypes.c_ulonglong(), ctypes.c_uint32()
+        _lib.check(_lib.raw("nps_searcher_stats")(self.handle, ctypes.byref(calls), ctypes.byref(fallbacks), ctypes.byref(slots)))
+        return {"calls": calls.value, "fallbacks": fallbacks.value, "slots": slots.value}
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self._destroy(self.handle)
+            self.handle = None
+
+
+_searcher_lock = threading.Lock()
+SEARCHER_MAX_WORDS = 63
+
+
+def searcher_for(hashes):
+    """The single-query searcher cached on a DeviceArray table (created, and the table uploaded, on first
+    use), or None when the table is not a DeviceArray / is wider than the fast path supports."""
+    if not isinstance(hashes, DeviceArray):
+        return None
+    s = hashes._nps_searcher
+    if s is not None:
+        return s
+    if hashes.ndim != 2 or hashes.dtype != np.uint64 or not 1 <= hashes.shape[1] <= SEARCHER_MAX_WORDS:
+        return None
+    with _searcher_lock:
+        if hashes._nps_searcher is None:
+            dev, _ = u64_table(hashes, "hamming_top_n", ndim=2)
+            if dev.data_ptr() % 16:
+                return None
+            hashes._nps_searcher = Searcher(dev)
+    return hashes._nps_searcher
 
 
 def is_tensor(x) -> bool:
@@ -92,6 +165,7 @@ def u64_table(x, name: str, ndim: int | None = None):
     dev = t.from_numpy(arr.view(np.int64)).cuda()
     if isinstance(x, DeviceArray):
         x._nps_dev = dev
+        _freeze(x)
     return dev, True
 
 

@@ -46,13 +46,18 @@ _SIGS = {
     "nps_index_destroy": (None, [_vp]),
     "nps_index_query_top_n": (_int, [_vp, _vp, _u32, _u32, _int, _vp, _vp]),
     "nps_index_hamming": (_int, [_vp, _vp, _vp]),
+    "nps_searcher_create": (_int, [_vp, _u64, _u32, _int, ctypes.POINTER(_vp)]),
+    "nps_searcher_destroy": (None, [_vp]),
+    "nps_searcher_top_k": (_int, [_vp, _vp, _u32, _vp]),
+    "nps_searcher_query_vector": (_int, [_vp, _vp, _int, _u32, _vp, _u32, _u32, _vp]),
+    "nps_searcher_stats": (_int, [_vp, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(_u32)]),
     "nps_hamming": (_int, [_vp, _u64, _u32, _vp, _u32, _vp, _int, _vp]),
     "nps_hamming_top_n_workspace_bytes": (_sz, [_u64, _u32, _u32, _u32]),
     "nps_hamming_top_n": (_int, [_vp, _u64, _u32, _vp, _u32, _u32, _u64, _vp, _vp, _vp, _sz, _vp]),
     "nps_hamming_top_n_keys": (_int, [_vp, _u64, _u32, _vp, _u32, _u32, _u64, _vp, _vp, _sz, _vp]),
     "nps_top_n_merge_workspace_bytes": (_sz, [_u32, _u32, _u32]),
     "nps_top_n_merge": (_int, [_vp, _u32, _u32, _u32, _int, _vp, _vp, _vp, _sz, _vp]),
-    "nps_hamming_top_n_reference_workspace_bytes": (_sz, [_u64, _u32, _u32]),
+    "nps_hamming_top_n_reference_workspace_bytes": (_sz, [_u64, _u32, _u32, _u32]),
     "nps_hamming_top_n_reference": (_int, [_vp, _u64, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _sz, _vp]),
     "nps_num_unshared_bits": (_int, [_vp, _u64, _vp, _u64, _u64, _vp, _vp]),
     "nps_rerank_top_n": (_int, [_vp, _u64, _u32, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp]),

@@ -10,7 +10,10 @@ import numpy as np
 
 from np_sims import hamming_c, hamming_naive, hamming_top_10, hamming_top_cand, hamming_top_n
 from . import _lib
-from ._device import DeviceArray, attach, is_tensor, ptr, require_cuda, stream_ptr, to_host_u64
+from ._device import DeviceArray, attach, is_tensor, ptr, require_cuda, searcher_for, stream_ptr, to_host_u64
+
+
+_searcher_query_vector = _lib.raw("nps_searcher_query_vector")
 
 
 def random_projection(dims):
@@ -43,6 +46,8 @@ def _projections_device(projections):
     dev = t.from_numpy(arr).cuda()
     if isinstance(projections, DeviceArray):
         projections._nps_dev = dev
+        from ._device import _freeze
+        _freeze(projections)
     return dev
 
 
@@ -211,7 +216,27 @@ def query_pure_python(vector, hashes, projections, hamming_func=hamming_naive, n
 
 def query_with_hamming_top_n(vector, hashes, projections, hamming_func=hamming_c, n=10):
     """lsh.py:70-74 — (hamming_top_10 ids, None); `n` and `hamming_func` are ignored by the
-    reference and therefore here."""
+    reference and therefore here.  A NumPy vector against a resident table (what `lsh.index` returns)
+    is ONE C call: host vector in, float64 projection + sign + pack, K2R search, host ids out, all in
+    one CUDA graph on the calling thread's own stream (csrc/searcher.cu)."""
+    if (type(vector) is np.ndarray and vector.ndim == 1 and vector.dtype in (np.float32, np.float64)
+            and isinstance(hashes, DeviceArray)):
+        s = searcher_for(hashes)
+        if s is not None:
+            pc = s.proj
+            if pc is None or pc[0] is not projections:
+                P = _projections_device(projections)
+                if P.dim() != 2 or P.device != s.table.device:
+                    raise ValueError("projections must be a [num_projections, dims] matrix on the table's device")
+                pc = s.proj = (projections, P, P.data_ptr(), int(P.shape[0]), int(P.shape[1]))
+            if vector.shape[0] != pc[4]:
+                raise ValueError(f"shapes {(pc[3], pc[4])} and {tuple(vector.shape)} not aligned")
+            if pc[3] == 64 * s.words:
+                v = vector if vector.flags.c_contiguous else np.ascontiguousarray(vector)
+                out = np.empty(10, dtype=np.uint64)
+                _lib.check(_searcher_query_vector(s.handle, v.ctypes.data, int(v.dtype == np.float32), pc[4], pc[2],
+                                                  pc[3], 10, out.ctypes.data))
+                return out, None
     query_hash = _query_signature(vector, projections)
     best = hamming_top_10(hashes, query_hash)
     return _results_like_inputs(best, vector, hashes), None

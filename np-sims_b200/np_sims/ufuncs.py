@@ -15,9 +15,10 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib
-from ._device import empty, is_tensor, ptr, require_cuda, stream_ptr, to_host_u64, u64_table
+from ._device import DeviceArray, empty, is_tensor, ptr, require_cuda, searcher_for, stream_ptr, to_host_u64, u64_table
 
 UINT64_MAX = np.iinfo(np.uint64).max
+_searcher_top_k = _lib.raw("nps_searcher_top_k")
 
 
 def _prepare(hashes, query, name):
@@ -88,6 +89,17 @@ def hamming_top_n(hashes, query, n=10, return_distances=False, order="canonical"
     n = int(n)
     if not 1 <= n <= _lib.NPS_MAX_K:
         raise ValueError(f"n={n} outside [1, {_lib.NPS_MAX_K}]")
+    if (order == "reference" and not return_distances and not row_base and type(query) is np.ndarray
+            and query.ndim == 1 and query.dtype == np.uint64 and isinstance(hashes, DeviceArray)
+            and hashes.ndim == 2 and hashes.shape[1] == query.shape[0]):
+        # the reference's calling pattern (one NumPy query per call, often from many threads) over a
+        # resident table: one C call = one CUDA-graph launch on the calling thread's own stream
+        s = searcher_for(hashes)
+        if s is not None:
+            q = query if query.flags.c_contiguous else np.ascontiguousarray(query)
+            out = np.empty(n, dtype=np.uint64)
+            _lib.check(_searcher_top_k(s.handle, q.ctypes.data, n, out.ctypes.data))
+            return out
     H, Q, single, host = _prepare(hashes, query, "hamming_top_n")
     m, w, q = H.shape[0], H.shape[1], Q.shape[0]
     rows = t.empty((q, n), dtype=t.int64, device=H.device)
@@ -105,9 +117,9 @@ def hamming_top_n(hashes, query, n=10, return_distances=False, order="canonical"
             if row_base:
                 raise ValueError("row_base is only supported with order='canonical'")
             # [batch, m] distances live in the workspace: bound the batch to ~1 GiB
-            per_q = max(1, _lib.raw("nps_hamming_top_n_reference_workspace_bytes")(m, w, 1))
+            per_q = max(1, _lib.raw("nps_hamming_top_n_reference_workspace_bytes")(m, w, 1, n))
             batch = max(1, min(q, (1 << 30) // per_q))
-            ws_bytes = _lib.raw("nps_hamming_top_n_reference_workspace_bytes")(m, w, batch)
+            ws_bytes = _lib.raw("nps_hamming_top_n_reference_workspace_bytes")(m, w, batch, n)
             ws = t.empty(max(ws_bytes, 16), dtype=t.uint8, device=H.device)
             for q0 in range(0, q, batch):
                 nq = min(batch, q - q0)

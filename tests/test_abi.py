@@ -43,7 +43,11 @@ def test_workspace_queries_need_no_gpu():
     assert f(1000, 10, 1, 5000) == 0         # k > NPS_MAX_K
     assert "k=5000" in _lib.last_error()
     assert _lib.raw("nps_top_n_merge_workspace_bytes")(100, 8, 10) == 0
-    assert _lib.raw("nps_hamming_top_n_reference_workspace_bytes")(1000, 10, 2) >= 2 * 1000 * 2
+    g = _lib.raw("nps_hamming_top_n_reference_workspace_bytes")
+    assert g(1000, 10, 2, 10) >= 2 * 1000 * 2              # dense fallback rows are always included
+    assert g(400_000, 10, 1, 10) < 4 << 20                 # K2R blocks are small next to the table
+    assert g(25_000_000, 16, 1, 1000) >= 25_000_000 * 2
+    assert g(1000, 10, 2, 0) == 0 and g(1000, 0, 2, 10) == 0
 
 
 def test_reference_surface_names():
