@@ -27,7 +27,7 @@ FLAGS = [
 # (source, object suffix, extra defines)
 UNITS = (
     [("scan_inst.cu", f"scan_g{g}", [f"-DNPS_WGROUP={g}"]) for g in range(5)]
-    + [(f, f[:-3], []) for f in ("merge.cu", "hamming.cu", "replay.cu", "ref_scan.cu", "rerank.cu", "project_f64.cu", "project_tc.cu", "mma_scan.cu", "searcher.cu", "api.cu")]
+    + [(f, f[:-3], []) for f in ("merge.cu", "hamming.cu", "replay.cu", "ref_scan.cu", "hist_select.cu", "rerank.cu", "project_f64.cu", "project_tc.cu", "mma_scan.cu", "searcher.cu", "api.cu")]
 )
 
 

@@ -9,6 +9,7 @@
 #include "../../include/npsims_b200.h"
 #include "common.cuh"
 #include "hamming.cuh"
+#include "hist_select.cuh"
 #include "merge.cuh"
 #include "mma_scan.cuh"
 #include "project.cuh"
@@ -225,6 +226,14 @@ static bool choose_mma(uint64_t N, uint32_t W, uint32_t Q, uint32_t k, const Dev
     return mma_plan(N, W, Q, k, dev.sm_count, dev.smem_optin, mp);
 }
 
+// Few queries, large k: counting select on the distance histogram (hist_select.cuh) instead of sorted
+// candidate lists.  k <= 32 stays on K2's private lists (0.9 of the HBM roofline, one launch).
+static bool choose_hist(uint64_t N, uint32_t W, uint32_t Q, uint32_t k, const DeviceInfo& dev, HistPlan* hp) {
+    if (k <= 32 || W > kHistMaxWords || Q > 32 || N < 4096) return false;
+    *hp = hist_plan(N, W, Q, k, dev.sm_count, dev.smem_optin);
+    return hp->applicable;
+}
+
 struct TopNWorkspace {
     size_t keys_bytes, scratch_bytes, total;
 };
@@ -356,6 +365,21 @@ static int run_top_n(const uint64_t* d_hashes, uint64_t N, uint32_t W, const uin
         return NPS_OK;
     }
     g_last_path = NPS_SCAN_POPC;
+    HistPlan hp;
+    if (choose_hist(N, W, Q, k, dev, &hp)) {
+        if (ws_bytes < hp.total || !ws) return fail(NPS_EWORKSPACE, "workspace %zu bytes < required %zu", ws_bytes, hp.total);
+        if (reinterpret_cast<uintptr_t>(ws) & 255u) return fail(NPS_EINVAL, "workspace must be 256-byte aligned");
+        g_last_plan = ScanPlanInfo{hp.tile_rows, hp.tile_rows * W * 8, hp.stages, hp.q_tile, hp.num_qtiles, hp.chunk_rows,
+                                   hp.num_chunks, 0, hp.smem, hp.grid, W <= 32 ? 1u : 0u,
+                                   W <= 32 ? (uint32_t)rows_per_thread((int)W) : 1u};
+        if (g_profile) {
+            rc = profile_events();
+            if (rc) return rc;
+        }
+        NPS_CUDA(run_hist_top_n(hp, d_hashes, N, W, d_queries, Q, k, row_base, d_rows, d_dists, d_keys_out, ws, stream,
+                                g_profile ? g_ev : nullptr));
+        return NPS_OK;
+    }
     ScanPlan pl;
     rc = plan_scan(N, W, Q, k, dev.sm_count, dev.smem_optin, &pl);
     if (rc) return rc;
@@ -482,6 +506,8 @@ size_t nps_hamming_top_n_workspace_bytes(uint64_t num_hashes, uint32_t words, ui
         if (plan_repair(num_hashes, words, num_queries, k, dev, &rp) != NPS_OK) return 0;
         return align256(mp.total) + rp.ws_bytes;
     }
+    HistPlan hp;
+    if (choose_hist(num_hashes, words, num_queries, k, dev, &hp)) return hp.total;
     ScanPlan pl;
     if (plan_scan(num_hashes, words, num_queries, k, dev.sm_count, dev.smem_optin, &pl) != NPS_OK) return 0;
     return topn_workspace(pl, num_queries, k).total;
@@ -533,7 +559,7 @@ static RefWorkspace ref_workspace(uint64_t N, uint32_t W, uint32_t nq, uint32_t 
     w.plan = ref_plan(N, W, k, dev.sm_count, dev.smem_optin);
     w.elt = (64ull * W > 65535ull) ? 4 : 2;
     w.row_bytes = ((size_t)N * w.elt + 15) & ~(size_t)15;      // every query's distance row starts 16-byte aligned
-    w.fast_bytes = w.plan.applicable ? align256(kRefHeaderBytes + (size_t)nq * w.plan.ws_stride) : 0;
+    w.fast_bytes = w.plan.applicable ? align256(ref_zero_bytes(nq) + (size_t)nq * w.plan.ws_stride) : 0;
     w.total = w.fast_bytes + align256(w.row_bytes * nq);
     return w;
 }
@@ -569,7 +595,7 @@ int nps_hamming_top_n_reference(const uint64_t* d_hashes, uint64_t num_hashes, u
     if (fast) {
         // K2R: prefix kernel + streaming superset scan + replay by the last CTA (ref_scan.cuh)
         NPS_CUDA(run_ref_top_n(w.plan, d_hashes, num_hashes, words, d_queries, num_queries, k, d_out_rows, d_out_scores,
-                               d_workspace, s));
+                               d_workspace, /*zero_first=*/true, s));
         gate = reinterpret_cast<const uint32_t*>(d_workspace);   // fallback below runs only if a segment overflowed
         if (num_hashes <= kRefSmallRows) return NPS_OK;           // all prefix: nothing can overflow
     }

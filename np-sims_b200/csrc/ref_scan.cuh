@@ -38,7 +38,7 @@ constexpr uint32_t kRefMaxPrefix = 32768;
 constexpr uint32_t kRefMaxCap = 4096;        // entries per chunk segment
 constexpr uint32_t kRefMaxChunks = 4096;
 constexpr uint32_t kRefBatch = 4096;         // replay batch (entries / 4 x distances) staged in shared memory
-constexpr int kRefPrefixThreads = 1024;
+constexpr int kRefPrefixThreads = 512;        // R0: one prefix row per thread (512: 128 registers for the replay)
 
 struct RefParams {
     const uint64_t* hashes;    // [N, W]
@@ -46,6 +46,8 @@ struct RefParams {
     uint64_t* out_rows;        // [nq, k] slot order, NPS_NONE where never filled
     uint64_t* out_scores;      // [nq, k] nullable
     uint32_t* any_overflow;    // [1] set when any query's segment overflowed (gate of the fallback launches)
+    uint32_t* ctrl;            // [nq, 4] control words (kRefCtrl*)
+    uint32_t* hist;            // [nq, kRefBins] distance histogram of the prefix rows (zero between calls)
     uint8_t* ws;               // per-query blocks of ws_stride bytes
     unsigned long long ws_stride;
     unsigned long long N;
@@ -53,135 +55,170 @@ struct RefParams {
     uint32_t P;                // prefix rows (R0); P == N: no R1
     uint32_t tile_rows;        // R1 tile (generic-width kernel; the specialised one knows it)
     uint32_t chunk_tiles, num_chunks, cap, stages;
-    uint32_t off_pre, off_cnt, off_seg;   // byte offsets inside a query's block (ctrl words at 0)
+    uint32_t off_pre, off_cnt, off_seg;   // byte offsets inside a query's block
 };
-// ctrl words at the start of a query's block
-enum { kRefCtrlTau = 0, kRefCtrlDone = 1, kRefCtrlOverflow = 2 };
+// control words of a query.  The done counters and the histogram are left at zero by the call itself
+// (the last CTA cleans up), so a workspace only has to be zeroed once (ref_zero_bytes()).
+enum { kRefCtrlTau = 0, kRefCtrlDone = 1, kRefCtrlOverflow = 2, kRefCtrlPrefixDone = 3 };
 
 // shared memory the replay needs (slots + one batch)
 __host__ __device__ inline uint32_t ref_replay_smem(uint32_t k, uint32_t num_chunks) {
-    return ((k * 4 + 15u) & ~15u) + k * 8 + kRefBatch * 8 + (((num_chunks + 1) * 4 + 15u) & ~15u) + 64;
+    return ((k * 8 + 15u) & ~15u) + kRefBatch * 8 + (((num_chunks + 1) * 4 + 15u) & ~15u) + k * 4 + 64;
 }
 
 // ---------------------------------------------------------------------------------------------
-// The reference queue, held by warp 0 of the calling thread group.
+// The reference queue, held in the REGISTERS of warp 0 of the calling thread group.
+// Slot s is ONE 32-bit key  score << 11 | (2047 - s)  (score < 4096, s < 2048; a never-filled slot
+// has the all-ones score), so "the FIRST slot holding the maximum" (ufunc.c:163-169: strict '>'
+// keeps the lowest slot) is a plain integer maximum.  Lane l owns slots l, l + 32, ... (SPL of them,
+// SPL = 1 for the reference's k = 10) in registers and caches their maximum; one redux.sync gives the
+// queue's worst and its slot.  An insert = one shuffle of the candidate's distance, a predicated
+// register update + re-scan of SPL registers by the owner lane, the redux — no shared-memory round
+// trip on the serial path.  Row ids of the slots live in shared memory (written on insert, read once
+// at the end).
 // ---------------------------------------------------------------------------------------------
-struct ReplayQueue {
-    volatile uint32_t* score;   // [k] shared
-    volatile uint64_t* row;     // [k] shared
-    uint32_t k;
-    uint64_t lane_best;         // max over this lane's slots of (score << 32 | ~slot)
-    uint32_t worst, worst_slot; // warp-uniform
+constexpr uint32_t kRefSlotBits = 11;
+constexpr uint32_t kRefSlotMask = (1u << kRefSlotBits) - 1u;
+constexpr uint32_t kRefEmptyScore = 0xFFFFFFFFu >> kRefSlotBits;
 
-    // lane l owns slots l, l + 32, ...: an insert re-scans only the owner's k/32 slots
-    __device__ __forceinline__ void rescan_lane(int lane) {
-        uint64_t best = 0;
-        for (uint32_t i = lane; i < k; i += 32) {
-            const uint64_t key = ((uint64_t)score[i] << 32) | (0xFFFFFFFFu - i);
-            best = key > best ? key : best;
-        }
+template <int SPL>
+struct ReplayQueue {
+    uint32_t key[SPL];          // key[j]: slot j * 32 + lane (0 for slots >= k)
+    uint64_t* row;              // [k] shared
+    uint32_t lane_best;         // max over this lane's slots
+    uint32_t worst, worst_slot; // warp-uniform; worst == kRefEmptyScore: the queue is not full
+
+    __device__ __forceinline__ void rescan() {
+        uint32_t best = 0;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) best = key[j] > best ? key[j] : best;
         lane_best = best;
     }
-    // first slot holding the maximum (ufunc.c:163-169: strict '>' keeps the lowest slot)
     __device__ __forceinline__ void publish() {
-        uint64_t best = lane_best;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
-            best = other > best ? other : best;
-        }
-        worst = (uint32_t)(best >> 32);
-        worst_slot = 0xFFFFFFFFu - (uint32_t)best;
-    }
-    __device__ __forceinline__ void insert(uint32_t d, uint64_t r, int lane) {
-        const uint32_t slot = worst_slot;
-        if (lane == 0) {
-            score[slot] = d;
-            row[slot] = r;
-        }
-        __syncwarp();
-        if ((slot & 31u) == (uint32_t)lane) rescan_lane(lane);
-        publish();
+        const uint32_t best = __reduce_max_sync(0xffffffffu, lane_best);
+        worst = best >> kRefSlotBits;
+        worst_slot = kRefSlotMask - (best & kRefSlotMask);
     }
     // up to 32 candidates in row order, one per lane: each is tested against the LIVE worst
-    // (strict '<', ufunc.c:152)
+    // (strict '<', ufunc.c:152); d < 4096
     __device__ __forceinline__ void group(uint32_t d, uint64_t r, bool valid, int lane) {
         uint32_t pend = __ballot_sync(0xffffffffu, valid && d < worst);
         while (pend) {
             const int src = __ffs(pend) - 1;
-            const uint32_t sd = __shfl_sync(0xffffffffu, d, src);
-            const uint64_t sr = __shfl_sync(0xffffffffu, r, src);
-            insert(sd, sr, lane);
+            const uint32_t slot = worst_slot;
+            const uint32_t nk = (__shfl_sync(0xffffffffu, d, src) << kRefSlotBits) | (kRefSlotMask - slot);
+            if (lane == src) row[slot] = r;
+            const bool owner = (slot & 31u) == (uint32_t)lane;
+            const int js = (int)(slot >> 5);
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) key[j] = (owner && j == js) ? nk : key[j];
+            rescan();
+            publish();
             pend &= ~((2u << src) - 1u);
             pend &= __ballot_sync(0xffffffffu, valid && d < worst);
         }
     }
 };
 
-// Replay for query block `blk` by `nthreads` threads (a multiple of 32, warp 0 included) that meet
-// on named barrier `bar`.  smem: ref_replay_smem(k, num_chunks) bytes, 16-byte aligned.
-__device__ __forceinline__ void replay_ordered(const RefParams& p, uint8_t* blk, uint64_t* out_rows, uint64_t* out_scores,
-                                               uint8_t* smem, int tid, int nthreads, uint32_t bar) {
-    const uint32_t k = p.k;
-    uint32_t* score_s = reinterpret_cast<uint32_t*>(smem);
-    uint64_t* row_s = reinterpret_cast<uint64_t*>(smem + ((k * 4 + 15u) & ~15u));
-    uint64_t* buf = row_s + k;                                                  // [kRefBatch]
+struct ReplayArgs {
+    uint8_t* blk;               // the query's workspace block
+    uint64_t* out_rows;         // [k]
+    uint64_t* out_scores;       // [k] nullable
+    uint32_t k, P, num_chunks, cap, off_pre, off_cnt, off_seg;
+};
+
+// Replay by `nthreads` threads (a multiple of 32, warp 0 included) that meet on named barrier `bar`.
+// smem: ref_replay_smem(k, num_chunks) bytes, 16-byte aligned.
+template <int SPL>
+__device__ __forceinline__ void replay_ordered(const ReplayArgs& a, uint8_t* smem, int tid, int nthreads, uint32_t bar) {
+    const uint32_t k = a.k;
+    uint64_t* row_s = reinterpret_cast<uint64_t*>(smem);                        // [k]
+    uint64_t* buf = reinterpret_cast<uint64_t*>(smem + ((k * 8 + 15u) & ~15u)); // [kRefBatch]
     uint32_t* offs = reinterpret_cast<uint32_t*>(buf + kRefBatch);              // [num_chunks + 1]
-    const uint16_t* pre = reinterpret_cast<const uint16_t*>(blk + p.off_pre);
-    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(blk + p.off_cnt);
-    const uint64_t* seg = reinterpret_cast<const uint64_t*>(blk + p.off_seg);
+    uint32_t* key_out = offs + ((a.num_chunks + 1 + 3u) & ~3u);                 // [k] final keys
+    const uint16_t* pre = reinterpret_cast<const uint16_t*>(a.blk + a.off_pre); // 16-byte aligned
+    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(a.blk + a.off_cnt);
+    const uint64_t* seg = reinterpret_cast<const uint64_t*>(a.blk + a.off_seg);
     const int lane = tid & 31, warp = tid >> 5;
-    const uint32_t P = p.P;
+    const uint32_t P = a.P, NC = a.num_chunks;
 
     // ---- fill (ufunc.c:153-157): the first min(k, N) rows take slots 0.. in order
     const uint32_t filled = P < k ? P : k;
-    for (uint32_t i = tid; i < k; i += nthreads) {
-        score_s[i] = i < filled ? (uint32_t)__ldcg(pre + i) : 0xFFFFFFFFu;
-        row_s[i] = i < filled ? (uint64_t)i : kNone;
+    for (uint32_t i = tid; i < k; i += nthreads) row_s[i] = i < filled ? (uint64_t)i : kNone;
+    ReplayQueue<SPL> Q;
+    Q.row = row_s;
+    if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const uint32_t s = (uint32_t)j * 32u + lane;
+            const uint32_t sc = s < filled ? (uint32_t)__ldcg(pre + s) : kRefEmptyScore;
+            Q.key[j] = s < k ? ((sc << kRefSlotBits) | (kRefSlotMask - s)) : 0u;
+        }
+        Q.rescan();
+        Q.publish();
     }
-    // segment offsets (exclusive prefix of the counts), by warp 0
-    const uint32_t NC = p.num_chunks;
+    // segment offsets: counts -> shared (all threads, independent loads), exclusive scan by warp 0
+    for (uint32_t c0 = 0; c0 < NC; c0 += 4u * nthreads) {
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t c = c0 + j * nthreads + tid;
+            if (c < NC) v[j] = __ldcg(cnt + c);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t c = c0 + j * nthreads + tid;
+            if (c < NC) offs[c + 1] = v[j];
+        }
+    }
+    named_bar_sync_rt(bar, nthreads);
     if (warp == 0) {
         uint32_t run = 0;
         for (uint32_t c0 = 0; c0 < NC; c0 += 32) {
             const uint32_t c = c0 + lane;
-            const uint32_t v = c < NC ? __ldcg(cnt + c) : 0u;
+            const uint32_t v = c < NC ? offs[c + 1] : 0u;
             uint32_t inc = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += t;
             }
-            if (c < NC) offs[c] = run + inc - v;
+            __syncwarp();
+            if (c < NC) offs[c + 1] = run + inc;
             run += __shfl_sync(0xffffffffu, inc, 31);
         }
-        if (lane == 0) offs[NC] = run;
+        if (lane == 0) offs[0] = 0;
     }
     named_bar_sync_rt(bar, nthreads);
-    ReplayQueue Q;
-    Q.score = score_s;
-    Q.row = row_s;
-    Q.k = k;
-    Q.lane_best = 0;
-    Q.worst = 0xFFFFFFFFu;
-    Q.worst_slot = 0;
-    if (warp == 0) {
-        Q.rescan_lane(lane);
-        Q.publish();
-    }
 
-    // ---- phase A: prefix rows [filled, P), dense distances, 4 * kRefBatch per batch
+    // ---- phase A: prefix rows [filled, P), dense distances, 4 * kRefBatch per batch (16-byte loads)
     uint16_t* dbuf = reinterpret_cast<uint16_t*>(buf);
     constexpr uint32_t kABatch = kRefBatch * 4;
-    for (uint32_t base = filled; base < P; base += kABatch) {
+    for (uint32_t base = filled & ~7u; base < P; base += kABatch) {   // base stays a multiple of 8
         const uint32_t n = (P - base) < kABatch ? (P - base) : kABatch;
-        for (uint32_t i = tid; i < n; i += nthreads) dbuf[i] = __ldcg(pre + base + i);
+        const uint32_t nv = (n + 7u) >> 3;                            // reads up to 14 bytes past P: inside the block
+        const uint4* src = reinterpret_cast<const uint4*>(pre + base);
+        uint4* dst = reinterpret_cast<uint4*>(dbuf);
+        for (uint32_t i0 = 0; i0 < nv; i0 += 4u * nthreads) {
+            uint4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t i = i0 + j * nthreads + tid;
+                if (i < nv) v[j] = __ldcg(src + i);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t i = i0 + j * nthreads + tid;
+                if (i < nv) dst[i] = v[j];
+            }
+        }
         named_bar_sync_rt(bar, nthreads);
         if (warp == 0) {
             for (uint32_t i = 0; i < n; i += 32) {
                 const uint32_t e = i + lane;
-                const uint32_t d = e < n ? (uint32_t)dbuf[e] : 0xFFFFFFFFu;
-                Q.group(d, (uint64_t)(base + e), e < n, lane);
+                const bool valid = e < n && base + e >= filled;
+                const uint32_t d = e < n ? (uint32_t)dbuf[e] : 0u;
+                Q.group(d, (uint64_t)(base + e), valid, lane);
             }
         }
         named_bar_sync_rt(bar, nthreads);
@@ -191,15 +228,27 @@ __device__ __forceinline__ void replay_ordered(const RefParams& p, uint8_t* blk,
     const uint32_t M = offs[NC];
     for (uint32_t base = 0; base < M; base += kRefBatch) {
         const uint32_t n = (M - base) < kRefBatch ? (M - base) : kRefBatch;
-        for (uint32_t i = tid; i < n; i += nthreads) {
-            const uint32_t e = base + i;
-            uint32_t lo = 0, hi = NC;            // largest c with offs[c] <= e
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (offs[mid] <= e) lo = mid;
-                else hi = mid;
+        for (uint32_t i0 = 0; i0 < n; i0 += 4u * nthreads) {
+            uint64_t v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t i = i0 + j * nthreads + tid;
+                if (i < n) {
+                    const uint32_t e = base + i;
+                    uint32_t lo = 0, hi = NC;            // largest c with offs[c] <= e
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (offs[mid] <= e) lo = mid;
+                        else hi = mid;
+                    }
+                    v[j] = __ldcg(seg + (size_t)lo * a.cap + (e - offs[lo]));
+                }
             }
-            buf[i] = __ldcg(seg + (size_t)lo * p.cap + (e - offs[lo]));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t i = i0 + j * nthreads + tid;
+                if (i < n) buf[i] = v[j];
+            }
         }
         named_bar_sync_rt(bar, nthreads);
         if (warp == 0) {
@@ -211,11 +260,43 @@ __device__ __forceinline__ void replay_ordered(const RefParams& p, uint8_t* blk,
         }
         named_bar_sync_rt(bar, nthreads);
     }
+    if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const uint32_t s = (uint32_t)j * 32u + lane;
+            if (s < k) key_out[s] = Q.key[j];
+        }
+    }
+    named_bar_sync_rt(bar, nthreads);
     for (uint32_t i = tid; i < k; i += nthreads) {
         const uint64_t r = row_s[i];
-        out_rows[i] = r;
-        if (out_scores) out_scores[i] = r == kNone ? kNone : (uint64_t)score_s[i];
+        a.out_rows[i] = r;
+        if (a.out_scores) a.out_scores[i] = r == kNone ? kNone : (uint64_t)(key_out[i] >> kRefSlotBits);
     }
+}
+
+#ifdef NPS_REF_DEVICE_CODE
+// One out-of-line copy per translation unit (not one per width-specialised kernel): cold code, run once.
+__device__ __noinline__ static void replay_run(ReplayArgs a, uint8_t* smem, int tid, int nthreads, uint32_t bar) {
+    if (a.k <= 32) replay_ordered<1>(a, smem, tid, nthreads, bar);
+    else if (a.k <= 128) replay_ordered<4>(a, smem, tid, nthreads, bar);
+    else if (a.k <= 512) replay_ordered<16>(a, smem, tid, nthreads, bar);
+    else if (a.k <= 1024) replay_ordered<32>(a, smem, tid, nthreads, bar);
+    else replay_ordered<64>(a, smem, tid, nthreads, bar);
+}
+__device__ __forceinline__ ReplayArgs replay_args(const RefParams& p, uint32_t qi) {
+    ReplayArgs a;
+    a.blk = p.ws + (size_t)qi * p.ws_stride;
+    a.out_rows = p.out_rows + (size_t)qi * p.k;
+    a.out_scores = p.out_scores ? p.out_scores + (size_t)qi * p.k : nullptr;
+    a.k = p.k;
+    a.P = p.P;
+    a.num_chunks = p.num_chunks;
+    a.cap = p.cap;
+    a.off_pre = p.off_pre;
+    a.off_cnt = p.off_cnt;
+    a.off_seg = p.off_seg;
+    return a;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -252,7 +333,7 @@ __device__ __forceinline__ void ref_flush_chunk(uint64_t* emit, uint32_t* misc, 
     uint32_t n = lds32_volatile(&misc[0]);
     if (n > cap) {
         if (tid == 0) {
-            atomicExch(reinterpret_cast<uint32_t*>(blk) + kRefCtrlOverflow, 1u);
+            atomicExch(p.ctrl + 4 * blockIdx.y + kRefCtrlOverflow, 1u);
             atomicExch(p.any_overflow, 1u);
         }
         n = cap;
@@ -304,20 +385,21 @@ __device__ __forceinline__ void ref_flush_chunk(uint64_t* emit, uint32_t* misc, 
 
 // After the CTA's last chunk: the last CTA of the query to get here replays.
 __device__ __forceinline__ void ref_finish(const RefParams& p, uint8_t* blk, uint32_t* misc, uint8_t* smem, int tid) {
+    uint32_t* ctrl = p.ctrl + 4 * blockIdx.y;
     __threadfence();
     consumer_bar();
     if (tid == 0) {
-        const uint32_t prev = atomicAdd(reinterpret_cast<uint32_t*>(blk) + kRefCtrlDone, 1u);
+        const uint32_t prev = atomicAdd(ctrl + kRefCtrlDone, 1u);
         sts32_volatile(&misc[1], prev == gridDim.x - 1 ? 1u : 0u);
     }
     consumer_bar();
     if (lds32_volatile(&misc[1]) == 0u) return;
     __threadfence();
-    const uint32_t overflow = *reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint32_t*>(blk) + kRefCtrlOverflow);
+    if (tid == 0) ctrl[kRefCtrlDone] = 0;      // leave the counter clean for the next call
+    const uint32_t overflow = *reinterpret_cast<volatile uint32_t*>(ctrl + kRefCtrlOverflow);
     if (overflow) return;   // the caller's fallback produces the result
     consumer_bar();         // everyone has read misc before the replay reuses shared memory
-    replay_ordered(p, blk, p.out_rows + (size_t)blockIdx.y * p.k, p.out_scores ? p.out_scores + (size_t)blockIdx.y * p.k : nullptr,
-                   smem, tid, kConsumerThreads, 1);
+    replay_run(replay_args(p, blockIdx.y), smem, tid, kConsumerThreads, 1);
 }
 
 // Producer: streams the tiles of this CTA's chunks (rows [P + chunk * chunk_rows, ...)) through the ring.
@@ -398,7 +480,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) ref_scan_kernel(const RefPara
         if (lane == 0) ref_producer(p, TILE_ROWS, ROW_BYTES, stage_base, stage_stride, full, empty);
         return;
     }
-    const uint32_t tau = reinterpret_cast<const uint32_t*>(blk)[kRefCtrlTau];
+    const uint32_t tau = p.ctrl[4 * blockIdx.y + kRefCtrlTau];
     const uint32_t S = p.stages, cap = p.cap;
     const int rot = EVEN ? (((tid & 7) * G) >> 3) : 0;
     const uint32_t qaddr = smem_u32(q_s) + rot * 16;
@@ -503,7 +585,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) ref_scan_generic_kernel(const
         if (lane == 0) ref_producer(p, TILE_ROWS, ROW_BYTES, stage_base, stage_stride, full, empty);
         return;
     }
-    const uint32_t tau = reinterpret_cast<const uint32_t*>(blk)[kRefCtrlTau];
+    const uint32_t tau = p.ctrl[4 * blockIdx.y + kRefCtrlTau];
     const uint32_t S = p.stages, cap = p.cap;
     const unsigned long long chunk_rows = (unsigned long long)p.chunk_tiles * TILE_ROWS;
     uint32_t s = 0, ph = 0;
@@ -536,6 +618,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) ref_scan_generic_kernel(const
 }
 #endif  // NPS_SCAN_GENERIC
 
+#endif  // NPS_REF_DEVICE_CODE
+
 // host-side launcher table (scan_inst.cu)
 typedef cudaError_t (*RefLaunchFn)(const RefParams&, dim3 grid, size_t smem, cudaStream_t);
 RefLaunchFn ref_launcher_for_width(int words);   // nullptr if no specialisation (words > 32)
@@ -549,12 +633,16 @@ struct RefPlan {
     size_t ws_stride;       // bytes per query
 };
 RefPlan ref_plan(unsigned long long N, uint32_t W, uint32_t k, int sm_count, int smem_optin);
-// Enqueues R0 (+ R1).  ws: kRefHeaderBytes + num_queries * plan.ws_stride bytes, 256-byte aligned.  The
-// uint32 at ws[0] is non-zero afterwards iff some query's segment overflowed (results of the call are
-// then not final: the caller runs K5 + the dense replay, gated on that word).
-constexpr size_t kRefHeaderBytes = 256;
+// Workspace: [ref_zero_bytes(nq): overflow word, control words, histograms | nq * plan.ws_stride], 256-byte
+// aligned.  The first ref_zero_bytes(nq) bytes must be ZERO when run_ref_top_n is enqueued (zero_first
+// does it with one cudaMemsetAsync; a caller that owns the workspace zeroes it once, every call leaves it
+// clean).  The uint32 at ws[0] is non-zero afterwards iff some query's segment overflowed (results are then
+// not final: the caller runs K5 + the dense replay, gated on that word); it is reset by the next call.
+inline size_t ref_zero_bytes(uint32_t nq) {
+    return (((size_t)16 + (size_t)nq * 16 + 255) & ~(size_t)255) + (size_t)nq * kRefBins * 4;
+}
 cudaError_t run_ref_top_n(const RefPlan& pl, const uint64_t* d_hashes, unsigned long long N, uint32_t W,
                           const uint64_t* d_queries, uint32_t nq, uint32_t k, uint64_t* d_rows, uint64_t* d_scores,
-                          void* ws, cudaStream_t stream);
+                          void* ws, bool zero_first, cudaStream_t stream);
 
 }  // namespace nps

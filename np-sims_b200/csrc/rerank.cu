@@ -4,7 +4,8 @@
 // without materialising the gathered table: one CTA per query reads the candidate rows in place.
 //
 // Order: ascending (distance, row id) — the canonical rule of this library.  Candidate ids of
-// UINT64_MAX (padding of a short first phase) or beyond the table are ignored.
+// UINT64_MAX (padding of a short first phase) or beyond the table are ignored; a candidate listed more than
+// once counts once.
 #include "common.cuh"
 #include "rerank.cuh"
 
@@ -44,24 +45,45 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(const uint64_t* 
         keys[i] = key;
     }
     __syncthreads();
-    // bitonic sort, ascending (keys are unique per row; pads sort last)
-    for (uint32_t size = 2; size <= P; size <<= 1) {
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t i = tid; i < (P >> 1); i += kRerankThreads) {
-                const uint32_t pos = 2 * i - (i & (stride - 1));
-                const uint64_t a = keys[pos], b = keys[pos + stride];
-                const bool up = (pos & size) == 0;
-                if ((a > b) == up) {
-                    keys[pos] = b;
-                    keys[pos + stride] = a;
+    // bitonic sort, ascending (pads sort last)
+    auto sort_keys = [&]() {
+        for (uint32_t size = 2; size <= P; size <<= 1) {
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t i = tid; i < (P >> 1); i += kRerankThreads) {
+                    const uint32_t pos = 2 * i - (i & (stride - 1));
+                    const uint64_t a = keys[pos], b = keys[pos + stride];
+                    const bool up = (pos & size) == 0;
+                    if ((a > b) == up) {
+                        keys[pos] = b;
+                        keys[pos + stride] = a;
+                    }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
+    };
+    sort_keys();
+    // A candidate listed more than once (arbitrary caller lists; hamming_top_n never emits duplicates):
+    // equal keys are now neighbours — blank all but the first of each run and sort again, so the result
+    // is compact and the (k+1)-th distinct candidate moves up.
+    constexpr uint32_t kPerThread = 4096 / kRerankThreads;
+    bool dup[kPerThread];
+    bool any = false;
+#pragma unroll
+    for (uint32_t j = 0; j < kPerThread; ++j) {
+        const uint32_t i = tid + j * kRerankThreads;
+        dup[j] = i > 0 && i < P && keys[i] != kNone && keys[i] == keys[i - 1];
+        any |= dup[j];
+    }
+    if (__syncthreads_or(any)) {
+#pragma unroll
+        for (uint32_t j = 0; j < kPerThread; ++j)
+            if (dup[j]) keys[tid + j * kRerankThreads] = kNone;
+        __syncthreads();
+        sort_keys();
     }
     for (uint32_t i = tid; i < k; i += kRerankThreads) {
-        uint64_t key = i < P ? keys[i] : kNone;
-        if (i > 0 && i < P && key != kNone && keys[i - 1] == key) key = kNone;   // a candidate listed twice
+        const uint64_t key = i < P ? keys[i] : kNone;
         const size_t o = (size_t)q * k + i;
         out_rows[o] = key == kNone ? kNone : (key & ((1ull << kGlobalRowBits) - 1ull));
         if (out_dists) out_dists[o] = key == kNone ? kNone : (key >> kGlobalRowBits);

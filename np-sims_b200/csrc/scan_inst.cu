@@ -5,7 +5,10 @@
 #define NPS_SCAN_GENERIC 1
 #endif
 #include "scan.cuh"
+#define NPS_REF_DEVICE_CODE 1
 #include "ref_scan.cuh"
+#define NPS_HIST_DEVICE_CODE 1
+#include "hist_select.cuh"
 
 namespace nps {
 
@@ -31,7 +34,18 @@ static cudaError_t launch_ref_scan_w(const RefParams& p, dim3 grid, size_t smem,
     return cudaGetLastError();
 }
 
-#define NPS_DECL_GROUP(g) ScanLaunchFn scan_launcher_group##g(int words); RefLaunchFn ref_launcher_group##g(int words);
+template <int W>
+static cudaError_t launch_hist_scan_w(const HistParams& p, int grid, size_t smem, cudaStream_t stream) {
+    constexpr int R = rows_per_thread(W);
+    auto kern = hist_scan_kernel<W, R>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kScanThreads, smem, stream>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+#define NPS_DECL_GROUP(g) ScanLaunchFn scan_launcher_group##g(int words); RefLaunchFn ref_launcher_group##g(int words); HistLaunchFn hist_launcher_group##g(int words);
 NPS_DECL_GROUP(0) NPS_DECL_GROUP(1) NPS_DECL_GROUP(2) NPS_DECL_GROUP(3)
 
 #if NPS_WGROUP < 4
@@ -53,7 +67,16 @@ NPS_DECL_GROUP(0) NPS_DECL_GROUP(1) NPS_DECL_GROUP(2) NPS_DECL_GROUP(3)
             default: return nullptr;                                       \
         }                                                                  \
     }
-#define NPS_DEFINE_GROUP(g) NPS_DEFINE_GROUP_(g) NPS_DEFINE_RGROUP_(g)
+#define NPS_HCASE(w) case (NPS_WGROUP * 8 + w): return launch_hist_scan_w<NPS_WGROUP * 8 + w>;
+#define NPS_DEFINE_HGROUP_(g)                                              \
+    HistLaunchFn hist_launcher_group##g(int words) {                       \
+        switch (words) {                                                   \
+            NPS_HCASE(1) NPS_HCASE(2) NPS_HCASE(3) NPS_HCASE(4)            \
+            NPS_HCASE(5) NPS_HCASE(6) NPS_HCASE(7) NPS_HCASE(8)            \
+            default: return nullptr;                                       \
+        }                                                                  \
+    }
+#define NPS_DEFINE_GROUP(g) NPS_DEFINE_GROUP_(g) NPS_DEFINE_RGROUP_(g) NPS_DEFINE_HGROUP_(g)
 NPS_DEFINE_GROUP(NPS_WGROUP)
 #else
 ScanLaunchFn scan_launcher_for_width(int words) {
@@ -64,6 +87,23 @@ ScanLaunchFn scan_launcher_for_width(int words) {
         case 2: return scan_launcher_group2(words);
         default: return scan_launcher_group3(words);
     }
+}
+HistLaunchFn hist_launcher_for_width(int words) {
+    if (words < 1 || words > 32) return nullptr;
+    switch ((words - 1) / 8) {
+        case 0: return hist_launcher_group0(words);
+        case 1: return hist_launcher_group1(words);
+        case 2: return hist_launcher_group2(words);
+        default: return hist_launcher_group3(words);
+    }
+}
+cudaError_t launch_hist_scan_generic(const HistParams& p, int grid, size_t smem, cudaStream_t stream) {
+    cudaError_t e =
+        cudaFuncSetAttribute(hist_scan_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hist_scan_generic_kernel<<<grid, kScanThreads, smem, stream>>>(p);
+    count_launch();
+    return cudaGetLastError();
 }
 RefLaunchFn ref_launcher_for_width(int words) {
     if (words < 1 || words > 32) return nullptr;

@@ -163,6 +163,7 @@ int slot_reserve(nps_searcher* S, Slot* s, size_t in_bytes, uint32_t k, size_t w
         s->d_ws = nullptr;
         s->ws_bytes = 0;
         S_CUDA(cudaMalloc(&s->d_ws, ws_bytes));
+        S_CUDA(cudaMemsetAsync(s->d_ws, 0, ref_zero_bytes(1), s->stream));   // once: every call leaves it clean
         s->ws_bytes = ws_bytes;
         changed = true;
     }
@@ -185,7 +186,7 @@ int enqueue(nps_searcher* S, Slot* s, const GraphKey& key, const RefPlan& pl, si
         count_launch();
         S_CUDA(cudaGetLastError());
     }
-    S_CUDA(run_ref_top_n(pl, S->d_hashes, S->N, S->W, d_q, 1, key.k, s->d_rows, nullptr, s->d_ws, s->stream));
+    S_CUDA(run_ref_top_n(pl, S->d_hashes, S->N, S->W, d_q, 1, key.k, s->d_rows, nullptr, s->d_ws, /*zero_first=*/false, s->stream));
     S_CUDA(cudaMemcpyAsync(s->h_out, s->d_rows, (size_t)key.k * 8, cudaMemcpyDeviceToHost, s->stream));
     S_CUDA(cudaMemcpyAsync(s->h_out + key.k, s->d_ws, 4, cudaMemcpyDeviceToHost, s->stream));
     return NPS_OK;
@@ -221,7 +222,7 @@ int run_query(nps_searcher* S, const GraphKey& key, const void* host_in, size_t 
             S->free_slots.push_back(s);
         }
     } release{S, s};
-    int rc = slot_reserve(S, s, in_bytes, key.k, kRefHeaderBytes + pl.ws_stride);
+    int rc = slot_reserve(S, s, in_bytes, key.k, ref_zero_bytes(1) + pl.ws_stride);
     if (rc) return rc;
     memcpy(s->h_in, host_in, in_bytes);
     cudaGraphExec_t exec = nullptr;
