@@ -705,12 +705,31 @@ def run_b200(args, wl):
             return index.gather(index.query_local(sigs, k, return_distances=False), nq), None
         return index.query(sigs, k)
 
-    def step_device():
+    def step_plain():
         return search(lsh.hash_vectors(qvecs_dev, W))
 
+    # The step as ONE CUDA graph (np_sims.pipeline.GraphedQueryBatch: hash + scan phases + selects + gated
+    # repairs captured once, replayed per step; the all-gather of N > 1 stays outside the graph).
+    graphed = None
+    if (world == 1 or by_query) and not args.no_graph:
+        from np_sims.pipeline import GraphedQueryBatch
+        graphed = GraphedQueryBatch(H_local, W, num_queries=qhi - qlo, dims=wl["dims"], n=k,
+                                    return_distances=world == 1, vectors=qvecs_dev)
+
+    def finish(out):
+        if world == 1:
+            return out                                      # (rows, dists)
+        return index.gather(out, nq), None
+
+    def step_device():
+        return finish(graphed()) if graphed is not None else step_plain()
+
     def step_e2e():
-        sigs = lsh.hash_vectors(qvecs_pinned.to(dev, non_blocking=True), W)
-        rows, _ = search(sigs)
+        if graphed is not None:
+            graphed.vectors.copy_(qvecs_pinned, non_blocking=True)      # H2D of the step's query vectors
+            rows, _ = finish(graphed())
+        else:
+            rows, _ = search(lsh.hash_vectors(qvecs_pinned.to(dev, non_blocking=True), W))
         out_pinned.copy_(rows.view(torch.int64))            # D2H of the step's result (blocking)
         return out_pinned
 
@@ -721,6 +740,10 @@ def run_b200(args, wl):
     total_ms, launches, (w0, w1) = timer.run(step_device, args.steps, args.warmup)
     clocks = sampler.stop(w0, w1) if rank == 0 else None
     value = nq * args.steps / (total_ms * 1e-3)
+    plain_ms = None
+    if graphed is not None:       # the same step launch by launch (what the graph replays), for comparison
+        plain_ms, launches, _ = timer.run(step_plain, args.steps, 3)
+        plain_ms /= args.steps
     e2e_ms, _, _ = timer.run(step_e2e, args.steps, max(3, args.warmup // 2))
     e2e_value = nq * args.steps / (e2e_ms * 1e-3)
 
@@ -756,7 +779,7 @@ def run_b200(args, wl):
     scan_ms, merge_ms, phase_runs = [], [], []
     for i in range(max(3, min(args.steps, 10))):
         flush.fill_(i)
-        step_device()
+        step_plain()
         s_ms, m_ms = _lib.profile_last()
         scan_ms.append(s_ms)
         merge_ms.append(m_ms)
@@ -813,7 +836,8 @@ def run_b200(args, wl):
     else:
         plan = _lib.last_scan_plan()
         # algorithmic bytes of one scan launch: signatures + queries + results
-        alg_bytes = n_local * words * 8 + nq_local * words * 8 + nq_local * plan["num_chunks"] * k * 8
+        alg_bytes = n_local * words * 8 + nq_local * words * 8 + (
+            nq_local * n_local * 2 if plan["cap"] == 0 else nq_local * plan["num_chunks"] * k * 8)
         achieved_gbs = alg_bytes / (scan_avg * 1e-3) / 1e9
         popc32 = 2.0 * n_local * nq_local * words
         popc_peak = 148 * 16 * sm_mhz * 1e6
@@ -892,7 +916,7 @@ def run_b200(args, wl):
         assert hash_report["flipped_bits_final"] == 0, "K1T signatures differ from the float64 kernel"
         assert hash_report["flipped_bits_final_vs_float64_oracle"] == 0, "K1T signatures differ from the float64 oracle"
     # free the C2 working set before the large sub-records
-    del index, H_local, qvecs_dev, flush
+    del index, H_local, qvecs_dev, flush, graphed
     timer.flush = None
     torch.cuda.empty_cache()
 
@@ -908,7 +932,9 @@ def run_b200(args, wl):
             "data": "synthetic",
             "config": make_config(wl, world, shard),
             "step": "hash query batch (K1T) + batched scan/top-n (K2T tensor-core phases + select)" +
+                    (", replayed as one CUDA graph (np_sims.pipeline.GraphedQueryBatch)" if graphed is not None else "") +
                     ((" + all-gather of results" if by_query else " + all-gather + K4 merge") if world > 1 else ""),
+            "ms_per_step_launch_by_launch": plain_ms,
             "index_build_s": index_s,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
@@ -940,20 +966,27 @@ def stream_roofline(torch, np_sims, _lib, dev, hbm_peak, peak_src, rows=25_000_0
     for _ in range(3):
         np_sims.hamming_top_n(H, q, k)
     _lib.raw("nps_profile_enable")(1)
-    ms = []
+    ms, sel_ms = [], []
     for _ in range(reps):
         np_sims.hamming_top_n(H, q, k)
-        ms.append(_lib.profile_last()[0])
+        a, b_ = _lib.profile_last()
+        ms.append(a)
+        sel_ms.append(b_)
     _lib.raw("nps_profile_enable")(0)
     plan = _lib.last_scan_plan()
     avg = float(np.mean(ms))
-    alg = rows * words * 8 + words * 8 + plan["num_chunks"] * k * 8
+    hist = plan["cap"] == 0       # K2H (hist_select.cuh): distances out as uint16, selection by counting
+    alg = rows * words * 8 + words * 8 + (rows * 2 if hist else plan["num_chunks"] * k * 8)
     gbs = alg / (avg * 1e-3) / 1e9
-    out = {"kernel": f"scan_topk_kernel<W={words},R={plan['rows_per_thread']}>", "workload":
+    out = {"kernel": (f"hist_scan_kernel<W={words},R={plan['rows_per_thread']}> (H1 of K2H: table stream + uint16 distances "
+                      "+ histogram)" if hist else f"scan_topk_kernel<W={words},R={plan['rows_per_thread']}>"),
+           "algorithmic_bytes": alg, "workload":
            f"1 query x {rows} x {words * 64}-bit signatures ({rows * words * 8 / 1e9:.1f} GB, larger than L2), top-{k}",
            "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
            "frac_of_nominal_8TBs": gbs / 8000.0,
-           "ms_per_launch": avg, "best_ms": float(np.min(ms)), "peak_source": peak_src, "plan": plan}
+           "ms_per_launch": avg, "best_ms": float(np.min(ms)), "select_ms": float(np.mean(sel_ms)),
+           "frac_whole_call": rows * words * 8 / ((avg + float(np.mean(sel_ms))) * 1e-3) / 1e9 / hbm_peak,
+           "peak_source": peak_src, "plan": plan}
     # the reference's own API on the same table: hamming_top_10 (queue order), whole call device-timed
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ref_ms = []
@@ -993,6 +1026,7 @@ def main():
     ap.add_argument("--c3-rows", type=int, default=0, help="development: smaller C3 input")
     ap.add_argument("--c3-steps", type=int, default=5)
     ap.add_argument("--c3-check-rows", type=int, default=20_000)
+    ap.add_argument("--no-graph", action="store_true", help="time the step launch by launch instead of as a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
     args = ap.parse_args()

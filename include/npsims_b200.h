@@ -74,9 +74,14 @@ int nps_last_scan_plan(nps_scan_plan_t *out);
 #define NPS_SCAN_MMA 2
 int nps_set_scan_path(int path);
 int nps_last_scan_path(void);
+/* Tensor-core scan: CTA pairs (tcgen05 cta_group::2: one M = 256 MMA per two SMs of a TPC, each CTA
+ * holding half of the query tile).  mode 0: never; 1 (default): where the single-CTA plan is squeezed
+ * by shared memory (signatures from ~1024 bits); 2: always.  Process-wide; for measurements and
+ * tests — results are identical. */
+int nps_set_mma_pair(int mode);
 typedef struct nps_mma_plan {
     uint32_t n_tile, num_qtiles, cap, growth, a_stages, smem_bytes, num_phases, last_tiles,
-        last_tiles_per_chunk, last_num_chunks, last_grid, reserved;
+        last_tiles_per_chunk, last_num_chunks, last_grid, pair;
 } nps_mma_plan_t;
 int nps_last_mma_plan(nps_mma_plan_t *out);
 /* After a profiled call that took the tensor-core path: device duration of each phase's scan

@@ -226,10 +226,12 @@ static bool choose_mma(uint64_t N, uint32_t W, uint32_t Q, uint32_t k, const Dev
     return mma_plan(N, W, Q, k, dev.sm_count, dev.smem_optin, mp);
 }
 
-// Few queries, large k: counting select on the distance histogram (hist_select.cuh) instead of sorted
-// candidate lists.  k <= 32 stays on K2's private lists (0.9 of the HBM roofline, one launch).
+// Few queries (<= 32): counting select on the distance histogram (hist_select.cuh) instead of K2's sorted
+// candidate lists — any k at the cost of the table stream (measured, 16M rows x 640 bit, 1 query:
+// k = 10 / 100 / 1000 in 0.27 ms each; K2: 0.31 / 0.82 / 2.91 ms).  K2 + K3 remain for signatures wider
+// than 63 words, tiny tables, larger POPC batches and the gated overflow repair of the tensor-core path.
 static bool choose_hist(uint64_t N, uint32_t W, uint32_t Q, uint32_t k, const DeviceInfo& dev, HistPlan* hp) {
-    if (k <= 32 || W > kHistMaxWords || Q > 32 || N < 4096) return false;
+    if (W > kHistMaxWords || Q > 32 || N < 4096) return false;
     *hp = hist_plan(N, W, Q, k, dev.sm_count, dev.smem_optin);
     return hp->applicable;
 }
@@ -435,12 +437,18 @@ int nps_set_scan_path(int path) {
 
 int nps_last_scan_path(void) { return g_last_path; }
 
+int nps_set_mma_pair(int mode) {
+    if (mode < 0 || mode > 2) return fail(NPS_EINVAL, "bad pair mode %d", mode);
+    mma_set_pair_mode(mode);
+    return NPS_OK;
+}
+
 int nps_last_mma_plan(nps_mma_plan_t* out) {
     if (!out) return fail(NPS_EINVAL, "out is null");
     const MmaPlan& m = g_last_mma_plan;
     const MmaPhase& L = m.phase[m.num_phases ? m.num_phases - 1 : 0];
     *out = nps_mma_plan_t{m.n_tile, m.num_qtiles, m.cap, m.growth, m.a_stages, m.smem, m.num_phases,
-                          L.tiles, L.tiles_per_chunk, L.num_chunks, L.grid, 0};
+                          L.tiles, L.tiles_per_chunk, L.num_chunks, L.grid, m.pair};
     return NPS_OK;
 }
 

@@ -217,14 +217,28 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-template <bool kDense>
+// kPair: the CTA is one half of a CTA pair (cluster of 2 on one TPC).  The pair issues ONE
+// tcgen05.mma.cta_group::2 of M = 256 per signature word: this CTA supplies the 128 rows of ITS row tile
+// (tile 2j + rank of the phase) and HALF of the query tile (B rows [rank * NT/2, (rank + 1) * NT/2)) from
+// its own shared memory, and keeps its 128 accumulator rows x NT columns in its own TMEM.  Per MMA a CTA's
+// shared memory then serves 4 KB of A + 3.5 KB of B instead of 4 + 7 KB — the single-CTA kernel is bound by
+// exactly that traffic.  Only the leader (rank 0) issues; barriers that gate the issue
+// (A group full, accumulator free, query tile ready) live in the LEADER's shared memory and take
+// arrivals from both CTAs; barriers signalled by tcgen05.commit are multicast to both.
+template <bool kDense, bool kPair>
 __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw);
     const uint32_t W = p.words, KB = mma_kblocks(W), NT = p.n_tile;
-    const MmaSmem L = mma_smem_layout(W, NT, p.a_stages, p.p_stages);
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const uint32_t cta_id = kPair ? (blockIdx.x >> 1) : blockIdx.x;       // work is dealt to pairs
+    const uint32_t num_ctas = kPair ? (gridDim.x >> 1) : gridDim.x;
+    const uint32_t NB = kPair ? NT / 2u : NT;                             // B rows (queries) this CTA expands
+    const uint32_t qoff = rank * NB;                                      // ... starting at this column of the tile
+    const uint32_t ptiles = kPair ? (p.phase_tiles + 1u) / 2u : p.phase_tiles;   // loop units (tile pairs / tiles)
+    const MmaSmem L = mma_smem_layout(W, NT, p.a_stages, p.p_stages, kPair ? 1u : 0u);
     const uint32_t PS = p.p_stages;
     // A ring: each MMA issuer owns RG (1 or 2) groups of GS K-block stages, so that every
     // group barrier has exactly one consumer (mbarrier phase parity cannot alias).
@@ -235,8 +249,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
     uint64_t* p_empty = p_full + PS;
     uint64_t* g_full = p_empty + PS;
     uint64_t* g_empty = g_full + NG;
-    uint64_t* acc_full = g_empty + NG;      // [2]
-    uint64_t* acc_empty = acc_full + 2;     // [2]
+    // acc_full: TWO barriers per accumulator buffer, used alternately by the tiles of that buffer
+    // (tile m of buffer b -> acc_full[2 b + (m & 1)], phase m >> 1).  With two A groups per issuer the
+    // expanders run up to two tiles ahead of the MMAs of a buffer; a single barrier per buffer would then
+    // be waited on one phase ahead at item boundaries, which a parity wait reports as "done".
+    uint64_t* acc_full = g_empty + NG;      // [4]
+    uint64_t* acc_empty = acc_full + 4;     // [2]
     uint64_t* b_full = acc_empty + 2;       // [1]
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
     uint32_t* wcnt_s = reinterpret_cast<uint32_t*>(smem + L.wcnt_off);
@@ -247,22 +265,24 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
             mbar_init(&p_full[s], 1);
             mbar_init(&p_empty[s], kMmaExpWarps / 2);    // one expander set per stage
         }
+        constexpr uint32_t kCtas = kPair ? 2u : 1u;     // leader barriers count the arrivals of both CTAs
         for (uint32_t s = 0; s < NG; ++s) {
-            mbar_init(&g_full[s], kMmaExpWarps / 2);     // one expander set per issuer
+            mbar_init(&g_full[s], kCtas * (kMmaExpWarps / 2));     // one expander set per issuer (and CTA)
             mbar_init(&g_empty[s], 1);
         }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], kMmaEpiWarps);
-        }
-        mbar_init(b_full, kMmaExpWarps);
+        for (int b = 0; b < 4; ++b) mbar_init(&acc_full[b], 1);
+        for (int b = 0; b < 2; ++b) mbar_init(&acc_empty[b], kCtas * kMmaEpiWarps);
+        mbar_init(b_full, kCtas * kMmaExpWarps);
         fence_mbar_init();
     }
     if (tid < kMmaEpiWarps) wcnt_s[tid] = 0;
     for (uint32_t i = tid; i < kMmaTileRows * 32u / 4u; i += kMmaThreads)
         reinterpret_cast<uint32_t*>(smem + L.athr_off)[i] = 0x66666666u;   // E2M1 4.0 in every element
     fence_proxy_async_smem();
-    if (warp == kWarpMma) tmem_alloc(tmem_ptr_s, 512);
+    if (warp == kWarpMma) {
+        if constexpr (kPair) tmem_alloc_pair(tmem_ptr_s, 512);
+        else tmem_alloc(tmem_ptr_s, 512);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -277,6 +297,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if constexpr (kPair) cluster_sync_all();   // both CTAs' barriers and tensor memory are set up
 
     // Everything above touched only this CTA's shared and tensor memory; from here on the kernel reads
     // what the previous launch in the stream (the select of the phase before) wrote.
@@ -291,14 +312,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         reg_dec<kRegsMisc>();
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+            for (uint32_t item = cta_id; item < total_items; item += num_ctas) {
                 const uint32_t chunk = item / p.num_qtiles;
                 const uint32_t i0 = chunk * p.tiles_per_chunk;
-                const uint32_t i1 = min(i0 + p.tiles_per_chunk, p.phase_tiles);
+                const uint32_t i1 = min(i0 + p.tiles_per_chunk, ptiles);
                 for (uint32_t i = i0; i < i1; ++i) {
-                    const unsigned long long row0 = (unsigned long long)phase_tile(p, i) * kMmaTileRows;
+                    const uint32_t ti = kPair ? 2u * i + rank : i;      // this CTA's row tile of the phase
+                    const bool tile_ok = ti < p.phase_tiles;            // odd tile count: the last pair is half empty
+                    const unsigned long long row0 = (unsigned long long)phase_tile(p, tile_ok ? ti : 0u) * kMmaTileRows;
                     const unsigned long long left = p.N - row0;
-                    const uint32_t rows = left < (unsigned long long)kMmaTileRows ? (uint32_t)left : kMmaTileRows;
+                    const uint32_t rows = !tile_ok ? 0u : left < (unsigned long long)kMmaTileRows ? (uint32_t)left : kMmaTileRows;
                     mbar_wait(&p_empty[s], ph ^ 1u);
                     const uint32_t bytes = rows * row_bytes, bulk = bytes & ~15u;
                     const uint8_t* src = reinterpret_cast<const uint8_t*>(p.hashes) + row0 * row_bytes;
@@ -326,33 +349,45 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         // independent (different accumulators, different A groups), so no order is required.
         reg_dec<kRegsMisc>();
         const uint32_t mw = warp - kWarpMma;
-        const uint32_t idesc = umma_idesc_mxf4(kMmaTileRows, NT);
+        const uint32_t idesc = umma_idesc_mxf4(kPair ? 2u * kMmaTileRows : kMmaTileRows, NT);
+        auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t sa, uint32_t sb, uint32_t acc) {
+            if constexpr (kPair) umma_mxf4_pair(d, a, b, idesc, sa, sb, acc);
+            else umma_mxf4(d, a, b, idesc, sa, sb, acc);
+        };
+        auto commit = [&](uint64_t* bar) {
+            if constexpr (kPair) umma_commit_pair(bar);
+            else umma_commit(bar);
+        };
+        auto wait_in = [&](uint64_t* bar, uint32_t parity) {   // barriers with arrivals from both CTAs
+            if constexpr (kPair) mbar_wait_cluster(bar, parity);
+            else mbar_wait(bar, parity);
+        };
         const uint32_t sfa = tmem_base + kMmaSfCol, sfb = tmem_base + kMmaSfCol + 32u;
         const uint64_t a_desc0 = umma_desc_k_sw128(base + L.a_off);
         const uint64_t b_desc0 = umma_desc_k_sw128(base + L.b_off);
         const uint64_t athr_desc = umma_desc_k_noswizzle(base + L.athr_off, 128u, 256u);
         const uint64_t bthr_desc = umma_desc_k_noswizzle(base + L.bthr_off, 128u, 256u);
-        const uint64_t bthr2_desc = umma_desc_k_noswizzle(base + L.bthr_off + NT * 32u, 128u, 256u);
+        const uint64_t bthr2_desc = umma_desc_k_noswizzle(base + L.bthr_off + NB * 32u, 128u, 256u);
         uint32_t t_idx = 0, it_idx = 0, lg = 0;   // lg: groups consumed by this issuer
-        for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x, ++it_idx) {
+        for (uint32_t item = cta_id; item < total_items && rank == 0u; item += num_ctas, ++it_idx) {
             const uint32_t chunk = item / p.num_qtiles;
             const uint32_t i0 = chunk * p.tiles_per_chunk;
-            const uint32_t i1 = min(i0 + p.tiles_per_chunk, p.phase_tiles);
+            const uint32_t i1 = min(i0 + p.tiles_per_chunk, ptiles);
             bool b_ready = false;
             for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
                 const uint32_t buf = t_idx & 1u;
                 if (buf != mw) continue;
                 if (!b_ready) {
-                    mbar_wait(b_full, it_idx & 1u);
+                    wait_in(b_full, it_idx & 1u);
                     b_ready = true;
                 }
-                mbar_wait(&acc_empty[buf], ((t_idx >> 1) & 1u) ^ 1u);
+                wait_in(&acc_empty[buf], ((t_idx >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 if (lane == 0) NPS_TRACE(mw ? 3 : 0, 1);   // accumulator free
                 const uint32_t d_tmem = tmem_base + buf * NT;
                 for (uint32_t g = 0; g < GPT; ++g, ++lg) {
                     const uint32_t slot = mw * RG + (lg & (RG - 1u)), par = (lg >> (RG - 1u)) & 1u;
-                    mbar_wait(&g_full[slot], par);
+                    wait_in(&g_full[slot], par);
                     tc_fence_after();
                     if (lane == 0) NPS_TRACE(mw ? 3 : 0, 2);   // A group full
                     if (elect_one()) {
@@ -360,18 +395,18 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                         for (uint32_t kb = kb0; kb < kb1; ++kb) {
                             const uint32_t stage = slot * GS + (kb - kb0);
                             const uint64_t a_desc = a_desc0 + (uint64_t)((stage * kMmaAStageBytes) >> 4);
-                            const uint64_t b_desc = b_desc0 + (uint64_t)((kb * NT * kMmaKBlockBytes) >> 4);
+                            const uint64_t b_desc = b_desc0 + (uint64_t)((kb * NB * kMmaKBlockBytes) >> 4);
                             const uint32_t nw = min(4u, W - 4u * kb);   // one MMA (K = 64) per signature word
                             for (uint32_t j = 0; j < nw && !(p.debug & 4u); ++j)
-                                umma_mxf4(d_tmem, a_desc + 2u * j, b_desc + 2u * j, idesc, sfa, sfb, (kb | j) != 0u);
+                                mma(d_tmem, a_desc + 2u * j, b_desc + 2u * j, sfa, sfb, (kb | j) != 0u);
                         }
-                        umma_commit(&g_empty[slot]);                  // group reusable once these MMAs retire
+                        commit(&g_empty[slot]);                       // group reusable once these MMAs retire
                         if (g + 1 == GPT) {
                             if (!p.dense) {                                                                // ... - T
-                                umma_mxf4(d_tmem, athr_desc, bthr_desc, idesc, sfa, sfb, 1u);
-                                if (W > kMmaThrOneSlice) umma_mxf4(d_tmem, athr_desc, bthr2_desc, idesc, sfa, sfb, 1u);
+                                mma(d_tmem, athr_desc, bthr_desc, sfa, sfb, 1u);
+                                if (W > kMmaThrOneSlice) mma(d_tmem, athr_desc, bthr2_desc, sfa, sfb, 1u);
                             }
-                            umma_commit(&acc_full[buf]);              // accumulator complete -> epilogue
+                            commit(&acc_full[2u * buf + ((t_idx >> 1) & 1u)]);   // accumulator complete -> epilogue
                         }
                     }
                     __syncwarp();
@@ -395,12 +430,19 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
             }
         };
         static_assert(kMmaExpWarps == 8, "two expander sets of four warps");
-        uint32_t pph = 0, t_idx = 0, lg2[1] = {0};   // pph: parity of my packed stage; lg2[0]: groups produced by my set
-        for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+        auto arrive_in = [&](uint64_t* bar) {   // barriers the MMA issuer (leader CTA) waits on
+            if constexpr (kPair) mbar_arrive_leader(bar);
+            else mbar_arrive(bar);
+        };
+        // packed ring: PS (even) stages; my set's j-th tile sits in stage part + 2 * (j % (PS / 2)) — the producer
+        // fills stage t % PS for tile t, and t % 2 is the set
+        const uint32_t PH = PS >> 1;
+        uint32_t pcur = 0, pph = 0, t_idx = 0, lg2[1] = {0};   // pcur: my set's position in its half of the ring, pph: its parity
+        for (uint32_t item = cta_id; item < total_items; item += num_ctas) {
             const uint32_t chunk = item / p.num_qtiles, qt = item - chunk * p.num_qtiles;
-            const uint32_t q0 = qt * NT;
+            const uint32_t q0 = qt * NT + qoff;          // first query of MY part of the tile
             const uint32_t i0 = chunk * p.tiles_per_chunk;
-            const uint32_t i1 = min(i0 + p.tiles_per_chunk, p.phase_tiles);
+            const uint32_t i1 = min(i0 + p.tiles_per_chunk, ptiles);
             // B (query tile) is resident for the whole item; the previous item's MMAs must have
             // retired before it is overwritten.
             // Each expander set waits for ITS OWN buffer's last tile only — it has just expanded that tile,
@@ -408,12 +450,21 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
             // waiting on the other, possibly lagging, set's barrier can be two phases ahead of it and see
             // the stale parity as "done": measured as wrong results on 4 % of the C2 queries) — and the two
             // sets then meet on a named barrier.
+            // With two A groups per issuer the MMAs of my buffer may be up to TWO tiles behind my expansion:
+            // both of my last two tiles are waited for, each on its own barrier (never more than one phase
+            // outstanding per barrier, so the parity test stays unambiguous; a single barrier per buffer was
+            // waited on one phase ahead here, read as "done", and the query tile was overwritten under
+            // pending MMAs — wrong results for 64..512-bit signatures on large batches).
             if (t_idx > 0) {
                 const uint32_t last = ((t_idx - 1u) & 1u) == part ? t_idx - 1u : t_idx - 2u;   // my set's last tile
-                if (last < t_idx) mbar_wait(&acc_full[part], (last >> 1) & 1u);
+                if (last < t_idx) {
+                    const uint32_t ml = last >> 1;   // its index among the tiles of my buffer
+                    if (ml >= 1u) mbar_wait(&acc_full[2u * part + ((ml - 1u) & 1u)], ((ml - 1u) >> 1) & 1u);
+                    mbar_wait(&acc_full[2u * part + (ml & 1u)], (ml >> 1) & 1u);
+                }
             }
             named_bar_sync(2, kMmaExpWarps * 32);
-            for (uint32_t n = u; n < NT; n += kMmaTileRows) {
+            for (uint32_t n = u; n < NB; n += kMmaTileRows) {
                 const bool valid = q0 + n < p.Q;
                 const uint64_t* src = p.queries + (size_t)(valid ? q0 + n : 0) * W;
                 for (uint32_t kb = 0; kb < KB; ++kb) {
@@ -421,11 +472,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                     uint64_t w[4];
 #pragma unroll
                     for (uint32_t j = 0; j < 4; ++j) w[j] = j < nw ? __ldg(src + 4 * kb + j) : 0ull;
-                    expand(base + L.b_off + kb * NT * kMmaKBlockBytes, n, w, nw);
+                    expand(base + L.b_off + kb * NB * kMmaKBlockBytes, n, w, nw);
                 }
             }
             if (!p.dense && part == 0) {
-                for (uint32_t n = u; n < NT; n += kMmaTileRows) {
+                for (uint32_t n = u; n < NB; n += kMmaTileRows) {
                     uint32_t e[8];
                     int T1, T2;
                     thr_split(__ldg(p.thrT + q0 + n), W, T1, T2);
@@ -435,14 +486,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                     sts128(dst + 128u, e[4], e[5], e[6], e[7]);
                     if (W > kMmaThrOneSlice) {   // second slice
                         encode_thr(T2, e);
-                        sts128(dst + NT * 32u, e[0], e[1], e[2], e[3]);
-                        sts128(dst + NT * 32u + 128u, e[4], e[5], e[6], e[7]);
+                        sts128(dst + NB * 32u, e[0], e[1], e[2], e[3]);
+                        sts128(dst + NB * 32u + 128u, e[4], e[5], e[6], e[7]);
                     }
                 }
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(b_full);
+            if (lane == 0) arrive_in(b_full);
             // A tiles.  The expander warps work as TWO independent sets of kMmaExpWarps/2 warps, one per
             // MMA issuer / accumulator buffer (set s takes the tiles with t_idx % 2 == s, whose packed
             // rows always sit in stage s of the two-stage packed ring).  Expanding one tile is a latency
@@ -450,11 +501,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
             // warps together could not shorten; two tiles in flight hide half of it.
             for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
                 if ((t_idx & 1u) != part) continue;
-                const unsigned long long row0 = (unsigned long long)phase_tile(p, i) * kMmaTileRows;
-                const bool valid = row0 + u < p.N;
-                mbar_wait_relaxed(&p_full[part], pph);
+                const uint32_t pst = part + 2u * pcur;      // my packed stage for this tile
+                mbar_wait_relaxed(&p_full[pst], pph);
                 if (u == 0 && part == 0) NPS_TRACE(1, 3);   // packed tile landed
-                const uint64_t* my = reinterpret_cast<const uint64_t*>(smem + L.p_off + part * L.p_stride) + (size_t)u * W;
+                const uint64_t* my = reinterpret_cast<const uint64_t*>(smem + L.p_off + pst * L.p_stride) + (size_t)u * W;
                 uint32_t lg = lg2[0];
                 for (uint32_t g = 0; g < GPT; ++g, ++lg) {
                     const uint32_t slot = part * RG + (lg & (RG - 1u)), par = (lg >> (RG - 1u)) & 1u;
@@ -497,13 +547,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                     fence_proxy_async_smem();
                     if (u == 0 && part == 0) NPS_TRACE(1, 5);   // proxy fence done
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&g_full[slot]);
+                    if (lane == 0) arrive_in(&g_full[slot]);
                     if (u == 0 && part == 0) NPS_TRACE(1, 2);   // group written
                 }
                 lg2[0] = lg;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&p_empty[part]);
-                pph ^= 1u;
+                if (lane == 0) mbar_arrive(&p_empty[pst]);
+                if (++pcur == PH) {
+                    pcur = 0;
+                    pph ^= 1u;
+                }
             }
         }
     } else {
@@ -528,11 +581,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 const bool prof_on = p.trace != nullptr && blockIdx.x == 0;)
         uint32_t pend_q = 0xFFFFFFFFu, pend_pos = 0;   // append whose slot reservation is still in flight
         uint64_t pend_key = 0;
-        for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+        for (uint32_t item = cta_id; item < total_items; item += num_ctas) {
             const uint32_t chunk = item / p.num_qtiles, qt = item - chunk * p.num_qtiles;
             const uint32_t q0 = qt * NT + c0;          // first query of this warp's columns
             const uint32_t i0 = chunk * p.tiles_per_chunk;
-            const uint32_t i1 = min(i0 + p.tiles_per_chunk, p.phase_tiles);
+            const uint32_t i1 = min(i0 + p.tiles_per_chunk, ptiles);
             if constexpr (!kDense) {   // this warp's thresholds for the item's query tile
                 __syncwarp();
                 for (uint32_t c = lane; c < cpw; c += 32u) thr_s[c] = clamp_thr(__ldg(p.thrT + q0 + c), W);
@@ -540,13 +593,15 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
             }
             for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
                 const uint32_t buf = t_idx & 1u;
-                const unsigned long long row = (unsigned long long)phase_tile(p, i) * kMmaTileRows + r_in_tile;
-                const bool valid = row < p.N;
+                const uint32_t ti = kPair ? 2u * i + rank : i;      // this CTA's row tile of the phase
+                const bool tile_ok = ti < p.phase_tiles;
+                const unsigned long long row = (unsigned long long)phase_tile(p, tile_ok ? ti : 0u) * kMmaTileRows + r_in_tile;
+                const bool valid = tile_ok && row < p.N;
                 const uint64_t grow = p.row_base + row;
                 const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * NT + c0;
                 uint32_t staged = 0;   // survivors of this tile waiting in the staging buffer
                 NPS_DEV(const long long pc0 = prof_on ? clock64() : 0;)
-                mbar_wait_relaxed(&acc_full[buf], (t_idx >> 1) & 1u);
+                mbar_wait_relaxed(&acc_full[2u * buf + ((t_idx >> 1) & 1u)], (t_idx >> 2) & 1u);
                 tc_fence_after();
                 NPS_DEV(const long long pc1 = prof_on ? clock64() : 0; prof_wait += pc1 - pc0;)
                 if (ew == 0 && lane == 0) NPS_TRACE(2, 1);   // accumulator ready
@@ -558,10 +613,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 tmem_ld_wait();
                 if constexpr (kDense) {
                     // first phase: every distance of the tile goes to its fixed slot of the buffer
-                    const size_t slot = (size_t)i * kMmaTileRows + r_in_tile;
+                    const size_t slot = (size_t)ti * kMmaTileRows + r_in_tile;
 #pragma unroll
                     for (int j = 0; j < 56; ++j) {
-                        if ((uint32_t)j < cpw && q0 + j < p.Q) {
+                        if (tile_ok && (uint32_t)j < cpw && q0 + j < p.Q) {
                             const uint64_t d = (uint64_t)((bits - (int)__uint_as_float(v[j])) >> 1);
                             p.cand[(size_t)(q0 + j) * p.cap + slot] = valid ? ((d << kGlobalRowBits) | grow) : kNone;
                         }
@@ -605,7 +660,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                if (lane == 0) {
+                    if constexpr (kPair) mbar_arrive_leader(&acc_empty[buf]);
+                    else mbar_arrive(&acc_empty[buf]);
+                }
                 NPS_DEV(const long long pc2 = prof_on ? clock64() : 0; prof_tile += pc2 - pc1;)
                 if (ew == 0 && lane == 0) NPS_TRACE(2, 2);   // accumulator released
                 // Flush this warp's staging buffer, one entry per lane.  The atomic that reserves the
@@ -659,7 +717,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
 
     tc_fence_before();
     __syncthreads();
-    if (warp == kWarpMma) tmem_dealloc(tmem_base, 512);
+    if constexpr (kPair) cluster_sync_all();   // the peer's MMAs / remote arrivals no longer touch this CTA
+    if (warp == kWarpMma) {
+        if constexpr (kPair) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // Launch with (pdl = true) or without the programmatic-stream-serialization attribute.
@@ -680,13 +742,35 @@ static cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cud
 }
 
 cudaError_t launch_mma_scan(const MmaScanParams& p, int grid, size_t smem, cudaStream_t stream, bool pdl) {
-    auto kern = p.dense ? mma_scan_kernel<true> : mma_scan_kernel<false>;
+    auto kern = p.pair ? (p.dense ? mma_scan_kernel<true, true> : mma_scan_kernel<false, true>)
+                       : (p.dense ? mma_scan_kernel<true, false> : mma_scan_kernel<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = launch_pdl(kern, dim3(grid), dim3(kMmaThreads), smem, stream, pdl, p);
+    if (!p.pair) {
+        e = launch_pdl(kern, dim3(grid), dim3(kMmaThreads), smem, stream, pdl, p);
+    } else {   // clusters of two CTAs (one CTA pair per TPC); grid = 2 x pairs
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kMmaThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl ? 2u : 1u;
+        e = cudaLaunchKernelEx(&cfg, kern, p);
+    }
     count_launch();
     return e;
 }
+
+static int g_pair_mode = 1;   // 0: never, 1: where the single-CTA plan is squeezed by shared memory, 2: always
+void mma_set_pair_mode(int mode) { g_pair_mode = mode; }
 
 // =============================================================================================
 // mma_select_kernel — fold a phase's candidates into the running exact top-k of every query.
@@ -885,24 +969,42 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
     // groups; for wide signatures use smaller groups rather than a narrow query tile.
     const uint32_t KB = mma_kblocks(W);
     uint32_t n_tile = 0, gs_best = 0, rg_best = 0;
-    for (uint32_t gs = KB;; gs = (gs + 1) / 2) {
-        for (uint32_t nt = want; nt >= 32; nt -= 32) {
-            if (nt < 128 && nt < want && gs > 1) break;          // try smaller groups before narrow tiles
-            uint32_t rg = 0;
-            for (uint32_t cand = 2; cand >= 1; --cand)
-                if (mma_smem_layout(W, nt, gs * 2 * cand, 2).total <= (uint32_t)smem_optin) {
-                    rg = cand;
+    auto select_tile = [&](uint32_t pair_mode) {
+        n_tile = gs_best = rg_best = 0;
+        for (uint32_t gs = KB;; gs = (gs + 1) / 2) {
+            for (uint32_t nt = want; nt >= 32; nt -= 32) {
+                if (nt < 128 && nt < want && gs > 1) break;          // try smaller groups before narrow tiles
+                uint32_t rg = 0;
+                for (uint32_t cand = 2; cand >= 1; --cand)
+                    if (mma_smem_layout(W, nt, gs * 2 * cand, 2, pair_mode).total <= (uint32_t)smem_optin) {
+                        rg = cand;
+                        break;
+                    }
+                if (rg) {
+                    n_tile = nt;
+                    gs_best = gs;
+                    rg_best = rg;
                     break;
                 }
-            if (rg) {
-                n_tile = nt;
-                gs_best = gs;
-                rg_best = rg;
-                break;
             }
+            if (n_tile || gs == 1) break;
         }
-        if (n_tile || gs == 1) break;
-    }
+    };
+    // CTA pairs (cta_group::2): each CTA of a pair holds HALF of the query tile, which halves the B operand's
+    // shared-memory footprint and read traffic.  Measured (profiles/r02_pair_vs_single.txt): a win exactly where
+    // the single-CTA plan is squeezed by shared memory — a query tile narrower than asked for, or A groups
+    // smaller than a row tile (1024-bit signatures +6 %, 2048-bit +46 %) — and neutral to slightly slower where
+    // everything already fits (640-bit: -3 %, 256-bit: -7 %: the pair adds cross-CTA hand-offs to a kernel
+    // that is bound by instruction issue in the expander and epilogue warps, not by B traffic).  So: auto.
+    // Needs an even SM count (a pair shares a TPC) and at least two row tiles.
+    select_tile(0);
+    if (!n_tile) return false;
+    const bool squeezed = n_tile < want || gs_best < KB;
+    const bool can_pair = (sm_count % 2) == 0 && N > kMmaTileRows;
+    uint32_t pair = can_pair && (g_pair_mode == 2 || (g_pair_mode == 1 && squeezed)) ? 1u : 0u;
+    if (const char* e = dev_knob("NPS_MMA_PAIR")) pair = atoi(e) != 0 && can_pair ? 1u : 0u;   // development
+    if (pair) select_tile(1);
+    pl->pair = pair;
     if (!n_tile) return false;
     if (const char* e = dev_knob("NPS_MMA_GROUPS")) {     // development: "GS,RG"
         uint32_t gs = 0, rg = 0;
@@ -915,8 +1017,16 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
     pl->group_kb = gs_best;
     pl->ring_per_issuer = rg_best;
     pl->a_stages = gs_best * 2 * rg_best;
-    pl->p_stages = 2;
-    pl->smem = mma_smem_layout(W, n_tile, pl->a_stages, 2).total;
+    // packed-row ring: two stages (one per expander set) hide nothing of the bulk-copy latency — a set's next
+    // tile is requested only when it has finished expanding the current one; take up to 8 if they fit
+    uint32_t ps = 2;
+    while (ps < 8 && mma_smem_layout(W, n_tile, pl->a_stages, ps + 2, pair).total <= (uint32_t)smem_optin) ps += 2;
+    if (const char* e = dev_knob("NPS_MMA_PSTAGES")) {   // development
+        const uint32_t v = (uint32_t)atoi(e);
+        if (v >= 2 && v % 2 == 0 && mma_smem_layout(W, n_tile, pl->a_stages, v, pair).total <= (uint32_t)smem_optin) ps = v;
+    }
+    pl->p_stages = ps;
+    pl->smem = mma_smem_layout(W, n_tile, pl->a_stages, ps, pair).total;
     pl->num_qtiles = (Q + n_tile - 1) / n_tile;
     pl->q_pad = pl->num_qtiles * n_tile;
     // ---- candidate capacity and phase growth: expected survivors per phase ~ k * growth <= cap / 4
@@ -967,16 +1077,19 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
             P.skip_mod = g;
             P.tiles = J - (J + g - 1) / g;
         }
-        // chunks: balance waves of (chunk, query tile) items over the SMs; ~1.5 tiles of fixed
-        // cost per item (query-tile expansion + pipeline drain)
+        // chunks: balance waves of (chunk, query tile) items over the SMs (CTA pairs: over the SM
+        // pairs, in units of two row tiles); ~1.5 units of fixed cost per item (query-tile expansion +
+        // pipeline drain)
+        const uint32_t units = pair ? (P.tiles + 1u) / 2u : P.tiles;
+        const uint32_t workers = pair ? (uint32_t)sm_count / 2u : (uint32_t)sm_count;
         double best_cost = 1e300;
-        uint32_t best_tpc = P.tiles ? P.tiles : 1;
-        const uint32_t cmax = P.tiles < 4096u ? P.tiles : 4096u;
+        uint32_t best_tpc = units ? units : 1;
+        const uint32_t cmax = units < 4096u ? units : 4096u;
         for (uint32_t c = 1; c <= cmax; ++c) {
-            const uint32_t tpc = (P.tiles + c - 1) / c;
-            const uint32_t chunks = (P.tiles + tpc - 1) / tpc;
+            const uint32_t tpc = (units + c - 1) / c;
+            const uint32_t chunks = (units + tpc - 1) / tpc;
             const unsigned long long items = (unsigned long long)chunks * pl->num_qtiles;
-            const unsigned long long waves = (items + sm_count - 1) / sm_count;
+            const unsigned long long waves = (items + workers - 1) / workers;
             const double cost = (double)waves * ((double)tpc + 1.5);
             if (cost < best_cost) {
                 best_cost = cost;
@@ -984,9 +1097,10 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
             }
         }
         P.tiles_per_chunk = best_tpc;
-        P.num_chunks = P.tiles ? (P.tiles + best_tpc - 1) / best_tpc : 0;
+        P.num_chunks = units ? (units + best_tpc - 1) / best_tpc : 0;
         const unsigned long long items = (unsigned long long)P.num_chunks * pl->num_qtiles;
-        P.grid = (uint32_t)(items < (unsigned long long)sm_count ? items : (unsigned long long)sm_count);
+        const uint32_t busy = (uint32_t)(items < (unsigned long long)workers ? items : (unsigned long long)workers);
+        P.grid = pair ? 2u * busy : busy;
     }
     // ---- workspace
     size_t off = 0;
@@ -1022,7 +1136,12 @@ cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned 
     if (e != cudaSuccess) return e;
     // Programmatic dependent launch between the back-to-back scan / select launches, unless per-phase
     // events are being recorded between them (profiling) or NPS_NO_PDL is set (development).
-    const bool use_pdl = phase_events == nullptr && dev_knob("NPS_NO_PDL") == nullptr;
+    // ... nor under stream capture (a CUDA graph already removes the launch gaps; programmatic edges are not
+    // needed there).
+    cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap_status) != cudaSuccess) cap_status = cudaStreamCaptureStatusNone;
+    const bool use_pdl = phase_events == nullptr && dev_knob("NPS_NO_PDL") == nullptr &&
+                         cap_status == cudaStreamCaptureStatusNone;
     for (uint32_t ph = 0; ph < pl.num_phases; ++ph) {
         const MmaPhase& P = pl.phase[ph];
         const bool last = ph + 1 == pl.num_phases;
@@ -1052,6 +1171,7 @@ cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned 
             sp.p_stages = pl.p_stages;
             sp.group_kb = pl.group_kb;
             sp.ring_per_issuer = pl.ring_per_issuer;
+            sp.pair = pl.pair;
             sp.trace = nullptr;
             const char* trace_path = dev_knob("NPS_MMA_TRACE");
             const char* trace_phase = dev_knob("NPS_MMA_TRACE_PHASE");

@@ -37,6 +37,7 @@ _SIGS = {
     "nps_launch_count": (ctypes.c_ulonglong, []),
     "nps_set_scan_path": (_int, [_int]),
     "nps_last_scan_path": (_int, []),
+    "nps_set_mma_pair": (_int, [_int]),
     "nps_last_mma_plan": (_int, [_vp]),
     "nps_profile_last_phases": (_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_u32), _u32, ctypes.POINTER(_u32)]),
     "nps_top_n_overflow_count": (_int, [_vp, _vp, ctypes.POINTER(ctypes.c_uint32)]),
@@ -89,10 +90,10 @@ class ScanPlan(ctypes.Structure):
 class MmaPlan(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint32) for n in (
         "n_tile", "num_qtiles", "cap", "growth", "a_stages", "smem_bytes", "num_phases", "last_tiles",
-        "last_tiles_per_chunk", "last_num_chunks", "last_grid", "reserved")]
+        "last_tiles_per_chunk", "last_num_chunks", "last_grid", "pair")]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
 def last_mma_plan() -> dict:

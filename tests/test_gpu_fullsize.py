@@ -36,13 +36,14 @@ def test_c2_full_size_vs_oracle(nps, family):
         if family == "mma":
             rows, dists = nps.hamming_top_n(H, Q, 10, return_distances=True)
             assert _lib.raw("nps_last_scan_path")() == _lib.SCAN_MMA
-            rows, dists = rows[torch.from_numpy(sel).cuda()], dists[torch.from_numpy(sel).cuda()]
+            rows = rows.view(torch.int64)[torch.from_numpy(sel).cuda()]
+            dists = dists.view(torch.int64)[torch.from_numpy(sel).cuda()]
         else:       # the XOR+POPC family is 20x slower on this batch: only the checked queries
             rows, dists = nps.hamming_top_n(H, Q[torch.from_numpy(sel).cuda()].contiguous(), 10, return_distances=True)
             assert _lib.raw("nps_last_scan_path")() == _lib.SCAN_POPC
     finally:
         _lib.set_scan_path(prev)
-    rows, dists = rows.cpu().numpy().view(np.uint64), dists.cpu().numpy().view(np.uint64)
+    rows, dists = rows.view(torch.int64).cpu().numpy().view(np.uint64), dists.view(torch.int64).cpu().numpy().view(np.uint64)
     for j, i in enumerate(sel):
         want_r, want_d = oracle.top_k_canonical(h, q[i], 10)
         assert np.array_equal(rows[j], want_r), (family, i)
@@ -110,3 +111,35 @@ def test_rerank_duplicate_candidates_are_compacted(nps):
         want_d[:len(order)] = d[order]
         assert np.array_equal(rows[i], want_r), i
         assert np.array_equal(dists[i], want_d), i
+
+
+@pytest.mark.parametrize("w", [1, 4, 5, 8])
+@pytest.mark.parametrize("pair", [0, 1])
+def test_narrow_signatures_large_batch_vs_oracle(nps, w, pair):
+    """64..512-bit signatures get two A groups per MMA issuer, so the expanders run two tiles ahead of the
+    tensor core.  At work-item boundaries that once let the query tile be overwritten under pending MMAs
+    (a parity wait one phase ahead reads as "done"): a few wrong results per thousand queries, only on
+    shapes with many work items per CTA — every smaller test was green.  So: 1M rows x 2000 queries,
+    checked against the ORACLE, single-CTA and CTA-pair MMAs."""
+    import torch
+    from np_sims import _lib
+    rng = np.random.default_rng(50 + w)
+    n, nq, k = 1_000_000, 2000, 10
+    h = rng.integers(0, 2**64, size=(n, w), dtype=np.uint64)
+    q = rng.integers(0, 2**64, size=(nq, w), dtype=np.uint64)
+    H, Q = torch.from_numpy(h.view(np.int64)).cuda(), torch.from_numpy(q.view(np.int64)).cuda()
+    prev = _lib.set_scan_path(_lib.SCAN_MMA)
+    _lib.raw("nps_set_mma_pair")(2 if pair else 0)
+    try:
+        for rep in range(3):
+            rows, dists = nps.hamming_top_n(H, Q, k, return_distances=True)
+            assert _lib.raw("nps_last_scan_path")() == _lib.SCAN_MMA
+            rows = rows.view(torch.int64).cpu().numpy().view(np.uint64)
+            dists = dists.view(torch.int64).cpu().numpy().view(np.uint64)
+            for i in rng.choice(nq, size=48, replace=False):
+                want_r, want_d = oracle.top_k_canonical(h, q[i], k)
+                assert np.array_equal(rows[i], want_r), (w, pair, rep, i)
+                assert np.array_equal(dists[i], want_d), (w, pair, rep, i)
+    finally:
+        _lib.raw("nps_set_mma_pair")(1)
+        _lib.set_scan_path(prev)

@@ -103,4 +103,8 @@ def test_hist_select_is_the_path_taken(nps):
     assert _lib.raw("nps_launch_count")() - before == 3      # H1 scan, H2 count, H3 emit + sort
     before = _lib.raw("nps_launch_count")()
     nps.hamming_top_n(H, Q, 10)
-    assert _lib.raw("nps_launch_count")() - before == 2      # K2 scan + K3 merge
+    assert _lib.raw("nps_launch_count")() - before == 3      # small k takes the same path
+    small = H[:1000].contiguous()
+    before = _lib.raw("nps_launch_count")()
+    nps.hamming_top_n(small, Q, 10)
+    assert _lib.raw("nps_launch_count")() - before == 2      # tiny table: K2 scan + K3 merge

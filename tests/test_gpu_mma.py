@@ -20,11 +20,14 @@ def nps():
     return np_sims
 
 
-@pytest.fixture()
-def force_mma():
+@pytest.fixture(params=["pair", "single"])
+def force_mma(request):
+    """Tensor-core family forced, once with CTA pairs (cta_group::2, the default) and once with single-CTA MMAs."""
     from np_sims import _lib
     prev = _lib.set_scan_path(_lib.SCAN_MMA)
+    _lib.raw("nps_set_mma_pair")(2 if request.param == "pair" else 0)
     yield _lib
+    _lib.raw("nps_set_mma_pair")(1)
     _lib.set_scan_path(prev)
 
 
