@@ -916,7 +916,9 @@ def run_b200(args, wl):
         assert hash_report["flipped_bits_final"] == 0, "K1T signatures differ from the float64 kernel"
         assert hash_report["flipped_bits_final_vs_float64_oracle"] == 0, "K1T signatures differ from the float64 oracle"
     # free the C2 working set before the large sub-records
-    del index, H_local, qvecs_dev, flush, graphed
+    used_graph = graphed is not None
+    graphed = None
+    del index, H_local, qvecs_dev, flush
     timer.flush = None
     torch.cuda.empty_cache()
 
@@ -932,7 +934,7 @@ def run_b200(args, wl):
             "data": "synthetic",
             "config": make_config(wl, world, shard),
             "step": "hash query batch (K1T) + batched scan/top-n (K2T tensor-core phases + select)" +
-                    (", replayed as one CUDA graph (np_sims.pipeline.GraphedQueryBatch)" if graphed is not None else "") +
+                    (", replayed as one CUDA graph (np_sims.pipeline.GraphedQueryBatch)" if used_graph else "") +
                     ((" + all-gather of results" if by_query else " + all-gather + K4 merge") if world > 1 else ""),
             "ms_per_step_launch_by_launch": plain_ms,
             "index_build_s": index_s,
