@@ -438,7 +438,7 @@ int nps_set_scan_path(int path) {
 int nps_last_scan_path(void) { return g_last_path; }
 
 int nps_set_mma_pair(int mode) {
-    if (mode < 0 || mode > 2) return fail(NPS_EINVAL, "bad pair mode %d", mode);
+    if (mode < 0 || mode > 3) return fail(NPS_EINVAL, "bad pair mode %d", mode);
     mma_set_pair_mode(mode);
     return NPS_OK;
 }
@@ -448,7 +448,7 @@ int nps_last_mma_plan(nps_mma_plan_t* out) {
     const MmaPlan& m = g_last_mma_plan;
     const MmaPhase& L = m.phase[m.num_phases ? m.num_phases - 1 : 0];
     *out = nps_mma_plan_t{m.n_tile, m.num_qtiles, m.cap, m.growth, m.a_stages, m.smem, m.num_phases,
-                          L.tiles, L.tiles_per_chunk, L.num_chunks, L.grid, m.pair};
+                          L.tiles, L.tiles_per_chunk, L.num_chunks, L.grid, m.pair | (m.qt << 8)};
     return NPS_OK;
 }
 

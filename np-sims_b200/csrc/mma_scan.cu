@@ -238,7 +238,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
     const uint32_t NB = kPair ? NT / 2u : NT;                             // B rows (queries) this CTA expands
     const uint32_t qoff = rank * NB;                                      // ... starting at this column of the tile
     const uint32_t ptiles = kPair ? (p.phase_tiles + 1u) / 2u : p.phase_tiles;   // loop units (tile pairs / tiles)
-    const MmaSmem L = mma_smem_layout(W, NT, p.a_stages, p.p_stages, kPair ? 1u : 0u);
+    // QT = 2 (pairs only): a work item covers TWO query tiles.  Each CTA then keeps its halves of both in shared
+    // memory (together what one CTA of the single-CTA kernel holds for one tile) and every expanded row tile
+    // is multiplied with both — half as many expansions per MMA.  MMA issuer h owns query tile h of the item
+    // and accumulator buffer h; an A slot is released when BOTH issuers' MMAs on it have retired.
+    const uint32_t QT = kPair ? p.qt_per_item : 1u;
+    const uint32_t num_qgroups = (p.num_qtiles + QT - 1u) / QT;
+    const MmaSmem L = mma_smem_layout(W, NT, p.a_stages, p.p_stages, kPair ? 1u : 0u, QT);
+    const uint32_t bthr_stride = NB * 32u * (W > kMmaThrOneSlice ? 2u : 1u);   // threshold operand tile of one query tile
     const uint32_t PS = p.p_stages;
     // A ring: each MMA issuer owns RG (1 or 2) groups of GS K-block stages, so that every
     // group barrier has exactly one consumer (mbarrier phase parity cannot alias).
@@ -268,7 +275,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         constexpr uint32_t kCtas = kPair ? 2u : 1u;     // leader barriers count the arrivals of both CTAs
         for (uint32_t s = 0; s < NG; ++s) {
             mbar_init(&g_full[s], kCtas * (kMmaExpWarps / 2));     // one expander set per issuer (and CTA)
-            mbar_init(&g_empty[s], 1);
+            mbar_init(&g_empty[s], QT);                            // one commit per issuer that read the group
         }
         for (int b = 0; b < 4; ++b) mbar_init(&acc_full[b], 1);
         for (int b = 0; b < 2; ++b) mbar_init(&acc_empty[b], kCtas * kMmaEpiWarps);
@@ -303,7 +310,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
     // what the previous launch in the stream (the select of the phase before) wrote.
     pdl_wait();
     pdl_launch_dependents();
-    const uint32_t total_items = p.num_chunks * p.num_qtiles;
+    const uint32_t total_items = p.num_chunks * num_qgroups;
     const uint32_t row_bytes = W * 8;
     NPS_DEV(uint32_t trace_n = 0;)
 
@@ -313,7 +320,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
             for (uint32_t item = cta_id; item < total_items; item += num_ctas) {
-                const uint32_t chunk = item / p.num_qtiles;
+                const uint32_t chunk = item / num_qgroups;
                 const uint32_t i0 = chunk * p.tiles_per_chunk;
                 const uint32_t i1 = min(i0 + p.tiles_per_chunk, ptiles);
                 for (uint32_t i = i0; i < i1; ++i) {
@@ -369,8 +376,49 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         const uint64_t bthr_desc = umma_desc_k_noswizzle(base + L.bthr_off, 128u, 256u);
         const uint64_t bthr2_desc = umma_desc_k_noswizzle(base + L.bthr_off + NB * 32u, 128u, 256u);
         uint32_t t_idx = 0, it_idx = 0, lg = 0;   // lg: groups consumed by this issuer
+        if (QT == 2u) {
+            // Two query tiles per item: this issuer multiplies EVERY row tile of the item with query tile mw into
+            // accumulator buffer mw (use index = tile count).  Plans with QT = 2 have one whole-tile A group per
+            // expander set: slot = tile & 1.
+            const uint64_t b_desc_h = b_desc0 + (uint64_t)((mw * KB * NB * kMmaKBlockBytes) >> 4);
+            const uint64_t bthr_h = umma_desc_k_noswizzle(base + L.bthr_off + mw * bthr_stride, 128u, 256u);
+            const uint64_t bthr2_h = umma_desc_k_noswizzle(base + L.bthr_off + mw * bthr_stride + NB * 32u, 128u, 256u);
+            const uint32_t d_tmem = tmem_base + mw * NT;
+            for (uint32_t item = cta_id; item < total_items && rank == 0u; item += num_ctas, ++it_idx) {
+                const uint32_t chunk = item / num_qgroups;
+                const uint32_t i0 = chunk * p.tiles_per_chunk;
+                const uint32_t i1 = min(i0 + p.tiles_per_chunk, ptiles);
+                if (i0 < i1) wait_in(b_full, it_idx & 1u);
+                for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
+                    wait_in(&acc_empty[mw], (t_idx & 1u) ^ 1u);
+                    tc_fence_after();
+                    if (lane == 0) NPS_TRACE(mw ? 3 : 0, 1);   // accumulator free
+                    const uint32_t slot = t_idx & 1u;
+                    wait_in(&g_full[slot], (t_idx >> 1) & 1u);
+                    tc_fence_after();
+                    if (lane == 0) NPS_TRACE(mw ? 3 : 0, 2);   // A group full
+                    if (elect_one()) {
+                        for (uint32_t kb = 0; kb < KB; ++kb) {
+                            const uint64_t a_desc = a_desc0 + (uint64_t)(((slot * GS + kb) * kMmaAStageBytes) >> 4);
+                            const uint64_t b_desc = b_desc_h + (uint64_t)((kb * NB * kMmaKBlockBytes) >> 4);
+                            const uint32_t nw = min(4u, W - 4u * kb);
+                            for (uint32_t j = 0; j < nw && !(p.debug & 4u); ++j)
+                                mma(d_tmem, a_desc + 2u * j, b_desc + 2u * j, sfa, sfb, (kb | j) != 0u);
+                        }
+                        commit(&g_empty[slot]);          // the slot is free once BOTH issuers' MMAs on it have retired
+                        if (!p.dense) {
+                            mma(d_tmem, athr_desc, bthr_h, sfa, sfb, 1u);
+                            if (W > kMmaThrOneSlice) mma(d_tmem, athr_desc, bthr2_h, sfa, sfb, 1u);
+                        }
+                        commit(&acc_full[2u * mw + (t_idx & 1u)]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) NPS_TRACE(mw ? 3 : 0, 3);   // issued + committed
+                }
+            }
+        } else
         for (uint32_t item = cta_id; item < total_items && rank == 0u; item += num_ctas, ++it_idx) {
-            const uint32_t chunk = item / p.num_qtiles;
+            const uint32_t chunk = item / num_qgroups;
             const uint32_t i0 = chunk * p.tiles_per_chunk;
             const uint32_t i1 = min(i0 + p.tiles_per_chunk, ptiles);
             bool b_ready = false;
@@ -386,7 +434,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 if (lane == 0) NPS_TRACE(mw ? 3 : 0, 1);   // accumulator free
                 const uint32_t d_tmem = tmem_base + buf * NT;
                 for (uint32_t g = 0; g < GPT; ++g, ++lg) {
-                    const uint32_t slot = mw * RG + (lg & (RG - 1u)), par = (lg >> (RG - 1u)) & 1u;
+                    const uint32_t slot = mw * RG + lg % RG, par = (lg / RG) & 1u;
                     wait_in(&g_full[slot], par);
                     tc_fence_after();
                     if (lane == 0) NPS_TRACE(mw ? 3 : 0, 2);   // A group full
@@ -439,8 +487,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         const uint32_t PH = PS >> 1;
         uint32_t pcur = 0, pph = 0, t_idx = 0, lg2[1] = {0};   // pcur: my set's position in its half of the ring, pph: its parity
         for (uint32_t item = cta_id; item < total_items; item += num_ctas) {
-            const uint32_t chunk = item / p.num_qtiles, qt = item - chunk * p.num_qtiles;
-            const uint32_t q0 = qt * NT + qoff;          // first query of MY part of the tile
+            const uint32_t chunk = item / num_qgroups, qg = item - chunk * num_qgroups;
             const uint32_t i0 = chunk * p.tiles_per_chunk;
             const uint32_t i1 = min(i0 + p.tiles_per_chunk, ptiles);
             // B (query tile) is resident for the whole item; the previous item's MMAs must have
@@ -458,12 +505,21 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
             if (t_idx > 0) {
                 const uint32_t last = ((t_idx - 1u) & 1u) == part ? t_idx - 1u : t_idx - 2u;   // my set's last tile
                 if (last < t_idx) {
-                    const uint32_t ml = last >> 1;   // its index among the tiles of my buffer
-                    if (ml >= 1u) mbar_wait(&acc_full[2u * part + ((ml - 1u) & 1u)], ((ml - 1u) >> 1) & 1u);
-                    mbar_wait(&acc_full[2u * part + (ml & 1u)], (ml >> 1) & 1u);
+                    if (QT == 2u) {   // that tile met both query tiles: buffers 0 and 1, use index = tile index
+                        for (uint32_t b = 0; b < 2u; ++b) {
+                            if (last >= 1u) mbar_wait(&acc_full[2u * b + ((last - 1u) & 1u)], ((last - 1u) >> 1) & 1u);
+                            mbar_wait(&acc_full[2u * b + (last & 1u)], (last >> 1) & 1u);
+                        }
+                    } else {
+                        const uint32_t ml = last >> 1;   // its index among the tiles of my buffer
+                        if (ml >= 1u) mbar_wait(&acc_full[2u * part + ((ml - 1u) & 1u)], ((ml - 1u) >> 1) & 1u);
+                        mbar_wait(&acc_full[2u * part + (ml & 1u)], (ml >> 1) & 1u);
+                    }
                 }
             }
             named_bar_sync(2, kMmaExpWarps * 32);
+            for (uint32_t h = 0; h < QT; ++h) {
+            const uint32_t q0 = (qg * QT + h) * NT + qoff;          // first query of MY part of query tile h
             for (uint32_t n = u; n < NB; n += kMmaTileRows) {
                 const bool valid = q0 + n < p.Q;
                 const uint64_t* src = p.queries + (size_t)(valid ? q0 + n : 0) * W;
@@ -472,7 +528,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                     uint64_t w[4];
 #pragma unroll
                     for (uint32_t j = 0; j < 4; ++j) w[j] = j < nw ? __ldg(src + 4 * kb + j) : 0ull;
-                    expand(base + L.b_off + kb * NB * kMmaKBlockBytes, n, w, nw);
+                    expand(base + L.b_off + (h * KB + kb) * NB * kMmaKBlockBytes, n, w, nw);
                 }
             }
             if (!p.dense && part == 0) {
@@ -481,7 +537,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                     int T1, T2;
                     thr_split(__ldg(p.thrT + q0 + n), W, T1, T2);
                     encode_thr(T1, e);
-                    const uint32_t dst = base + L.bthr_off + (n >> 3) * 256u + (n & 7u) * 16u;
+                    const uint32_t dst = base + L.bthr_off + h * bthr_stride + (n >> 3) * 256u + (n & 7u) * 16u;
                     sts128(dst, e[0], e[1], e[2], e[3]);
                     sts128(dst + 128u, e[4], e[5], e[6], e[7]);
                     if (W > kMmaThrOneSlice) {   // second slice
@@ -491,6 +547,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                     }
                 }
             }
+            }   // query tiles of the item
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) arrive_in(b_full);
@@ -507,7 +564,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                 const uint64_t* my = reinterpret_cast<const uint64_t*>(smem + L.p_off + pst * L.p_stride) + (size_t)u * W;
                 uint32_t lg = lg2[0];
                 for (uint32_t g = 0; g < GPT; ++g, ++lg) {
-                    const uint32_t slot = part * RG + (lg & (RG - 1u)), par = (lg >> (RG - 1u)) & 1u;
+                    const uint32_t slot = part * RG + lg % RG, par = (lg / RG) & 1u;
                     mbar_wait_relaxed(&g_empty[slot], par ^ 1u);
                     if (u == 0 && part == 0) NPS_TRACE(1, 1);   // group free
                     const uint32_t kb0 = g * GS, kb1 = min(kb0 + GS, KB);
@@ -573,7 +630,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         const uint32_t c0 = (ew >> 2) * cpw;
         const uint32_t qmask = (1u << (cpw / 8u)) - 1u;   // 8-column quarters that exist
         uint2* hits = reinterpret_cast<uint2*>(smem + L.hitk_off) + ew * (kMmaHitsPerWarp + 1);
-        float* thr_s = reinterpret_cast<float*>(smem + L.thr_off) + ew * 64u;
+        float* thr_s = reinterpret_cast<float*>(smem + L.thr_off) + ew * 64u * QT;   // [QT][64]
         const uint32_t lane_lt = (1u << lane) - 1u;
         const int bits = (int)(W * 64u);
         uint32_t t_idx = 0;
@@ -582,26 +639,32 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
         uint32_t pend_q = 0xFFFFFFFFu, pend_pos = 0;   // append whose slot reservation is still in flight
         uint64_t pend_key = 0;
         for (uint32_t item = cta_id; item < total_items; item += num_ctas) {
-            const uint32_t chunk = item / p.num_qtiles, qt = item - chunk * p.num_qtiles;
-            const uint32_t q0 = qt * NT + c0;          // first query of this warp's columns
+            const uint32_t chunk = item / num_qgroups, qg = item - chunk * num_qgroups;
             const uint32_t i0 = chunk * p.tiles_per_chunk;
             const uint32_t i1 = min(i0 + p.tiles_per_chunk, ptiles);
-            if constexpr (!kDense) {   // this warp's thresholds for the item's query tile
+            if constexpr (!kDense) {   // this warp's thresholds for the item's query tile(s)
                 __syncwarp();
-                for (uint32_t c = lane; c < cpw; c += 32u) thr_s[c] = clamp_thr(__ldg(p.thrT + q0 + c), W);
+                for (uint32_t h = 0; h < QT; ++h)
+                    for (uint32_t c = lane; c < cpw; c += 32u)
+                        thr_s[h * 64u + c] = clamp_thr(__ldg(p.thrT + (qg * QT + h) * NT + c0 + c), W);
                 __syncwarp();
             }
             for (uint32_t i = i0; i < i1; ++i, ++t_idx) {
-                const uint32_t buf = t_idx & 1u;
                 const uint32_t ti = kPair ? 2u * i + rank : i;      // this CTA's row tile of the phase
                 const bool tile_ok = ti < p.phase_tiles;
                 const unsigned long long row = (unsigned long long)phase_tile(p, tile_ok ? ti : 0u) * kMmaTileRows + r_in_tile;
                 const bool valid = tile_ok && row < p.N;
                 const uint64_t grow = p.row_base + row;
+              for (uint32_t h = 0; h < QT; ++h) {   // the row tile against each query tile of the item
+                // accumulator buffer and its use index: QT = 2 -> buffer h, every tile; else buffers alternate by tile
+                const uint32_t buf = QT == 2u ? h : (t_idx & 1u);
+                const uint32_t use = QT == 2u ? t_idx : (t_idx >> 1);
+                const uint32_t q0 = (qg * QT + h) * NT + c0;          // first query of this warp's columns
+                float* thr_h = thr_s + h * 64u;
                 const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * NT + c0;
                 uint32_t staged = 0;   // survivors of this tile waiting in the staging buffer
                 NPS_DEV(const long long pc0 = prof_on ? clock64() : 0;)
-                mbar_wait_relaxed(&acc_full[2u * buf + ((t_idx >> 1) & 1u)], (t_idx >> 2) & 1u);
+                mbar_wait_relaxed(&acc_full[2u * buf + (use & 1u)], (use >> 1) & 1u);
                 tc_fence_after();
                 NPS_DEV(const long long pc1 = prof_on ? clock64() : 0; prof_wait += pc1 - pc0;)
                 if (ew == 0 && lane == 0) NPS_TRACE(2, 1);   // accumulator ready
@@ -645,9 +708,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                         if (wm & 64u) stage_hits8<48>(v, (m & 64u) != 0u, lane, wn, hits, lane_lt);
                         // staging overflow (loose early-phase thresholds): redo this warp's columns exactly
                         if (wn > (uint32_t)kMmaHitsPerWarp) {
-                            rescan_group(t_addr, thr_s, q0, (int)min(cpw, 32u), grow, bits, valid, p.cnt, p.cand, p.cap);
+                            rescan_group(t_addr, thr_h, q0, (int)min(cpw, 32u), grow, bits, valid, p.cnt, p.cand, p.cap);
                             if (cpw > 32u)
-                                rescan_group(t_addr + 32u, thr_s + 32, q0 + 32u, (int)(cpw - 32u), grow, bits, valid, p.cnt,
+                                rescan_group(t_addr + 32u, thr_h + 32, q0 + 32u, (int)(cpw - 32u), grow, bits, valid, p.cnt,
                                              p.cand, p.cap);
                             wn = 0;
                         }
@@ -682,7 +745,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                         auto decode = [&](uint32_t e, uint32_t& q, uint64_t& key) {
                             const uint2 h = hits[e];
                             const uint32_t col = h.y >> 8;   // column within this warp's part
-                            const int dot = (int)(__uint_as_float(h.x) + thr_s[col]);
+                            const int dot = (int)(__uint_as_float(h.x) + thr_h[col]);
                             const uint64_t r = grow - lane + (h.y & 31u);
                             q = q0 + col;
                             key = ((uint64_t)((bits - dot) >> 1) << kGlobalRowBits) | r;
@@ -701,6 +764,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_scan_kernel(const MmaScanP
                     }
                     NPS_DEV(if (prof_on) prof_flush += clock64() - f0;)
                 }
+              }   // query tiles of the item
             }
         }
         if (pend_q != 0xFFFFFFFFu && pend_pos < p.cap) p.cand[(size_t)pend_q * p.cap + pend_pos] = pend_key;
@@ -769,7 +833,8 @@ cudaError_t launch_mma_scan(const MmaScanParams& p, int grid, size_t smem, cudaS
     return e;
 }
 
-static int g_pair_mode = 1;   // 0: never, 1: where the single-CTA plan is squeezed by shared memory, 2: always
+static int g_pair_mode = 1;   // 0: never; 1: auto (two query tiles per item where they fit, else pairs where the single-CTA
+                              // plan is squeezed by shared memory); 2: always; 3: always, one query tile per item
 void mma_set_pair_mode(int mode) { g_pair_mode = mode; }
 
 // =============================================================================================
@@ -1001,14 +1066,38 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
     if (!n_tile) return false;
     const bool squeezed = n_tile < want || gs_best < KB;
     const bool can_pair = (sm_count % 2) == 0 && N > kMmaTileRows;
-    uint32_t pair = can_pair && (g_pair_mode == 2 || (g_pair_mode == 1 && squeezed)) ? 1u : 0u;
+    uint32_t pair = can_pair && (g_pair_mode >= 2 || (g_pair_mode == 1 && squeezed)) ? 1u : 0u;
     if (const char* e = dev_knob("NPS_MMA_PAIR")) pair = atoi(e) != 0 && can_pair ? 1u : 0u;   // development
     if (pair) select_tile(1);
+    // Two query tiles per work item (pairs only): each CTA keeps its halves of BOTH tiles resident and every
+    // expanded row tile is multiplied with both, which halves the expansions per MMA — the expander warps'
+    // instructions and shared-memory stores are what bounds the single-tile kernel.  Needs the plan with
+    // whole-tile A groups, one per expander set, to still fit with the doubled B.
+    uint32_t qt = 1;
+    const char* pair_knob = dev_knob("NPS_MMA_PAIR");
+    const bool pair_off = g_pair_mode == 0 || (pair_knob != nullptr && atoi(pair_knob) == 0);
+    // Measured (profiles/r02_pair_vs_single.txt): exact, but NOT faster — 640-bit C2 last phase 0.608 ms against
+    // 0.566 ms single-CTA: the step is paced by the hand-off chain expand -> issue -> retire per A slot and by
+    // MMAs that run ~30 % slower while expander stores share the shared-memory port, not by the number of
+    // expansions.  Kept behind mode 2 (measurements, tests); the automatic plan does not use it.
+    const bool qt2_wanted = g_pair_mode == 2 || (pair_knob != nullptr && atoi(pair_knob) != 0);
+    if (!pair_off && qt2_wanted && can_pair && Q > want && dev_knob("NPS_MMA_QT1") == nullptr) {
+        for (uint32_t nt2 = want; nt2 >= 128 && nt2 + 32 >= want; nt2 -= 32)   // at most one step narrower
+            if (mma_smem_layout(W, nt2, KB * 2, 2, 1, 2).total <= (uint32_t)smem_optin && Q > nt2) {
+                pair = 1;
+                qt = 2;
+                n_tile = nt2;
+                gs_best = KB;
+                rg_best = 1;
+                break;
+            }
+    }
     pl->pair = pair;
+    pl->qt = qt;
     if (!n_tile) return false;
     if (const char* e = dev_knob("NPS_MMA_GROUPS")) {     // development: "GS,RG"
         uint32_t gs = 0, rg = 0;
-        if (sscanf(e, "%u,%u", &gs, &rg) == 2 && gs && (rg == 1 || rg == 2)) {
+        if (qt == 1 && sscanf(e, "%u,%u", &gs, &rg) == 2 && gs && rg >= 1 && rg <= 4) {
             gs_best = gs;
             rg_best = rg;
         }
@@ -1020,15 +1109,16 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
     // packed-row ring: two stages (one per expander set) hide nothing of the bulk-copy latency — a set's next
     // tile is requested only when it has finished expanding the current one; take up to 8 if they fit
     uint32_t ps = 2;
-    while (ps < 8 && mma_smem_layout(W, n_tile, pl->a_stages, ps + 2, pair).total <= (uint32_t)smem_optin) ps += 2;
+    while (ps < 8 && mma_smem_layout(W, n_tile, pl->a_stages, ps + 2, pair, qt).total <= (uint32_t)smem_optin) ps += 2;
     if (const char* e = dev_knob("NPS_MMA_PSTAGES")) {   // development
         const uint32_t v = (uint32_t)atoi(e);
-        if (v >= 2 && v % 2 == 0 && mma_smem_layout(W, n_tile, pl->a_stages, v, pair).total <= (uint32_t)smem_optin) ps = v;
+        if (v >= 2 && v % 2 == 0 && mma_smem_layout(W, n_tile, pl->a_stages, v, pair, qt).total <= (uint32_t)smem_optin) ps = v;
     }
     pl->p_stages = ps;
-    pl->smem = mma_smem_layout(W, n_tile, pl->a_stages, ps, pair).total;
+    pl->smem = mma_smem_layout(W, n_tile, pl->a_stages, ps, pair, qt).total;
     pl->num_qtiles = (Q + n_tile - 1) / n_tile;
-    pl->q_pad = pl->num_qtiles * n_tile;
+    const uint32_t num_qgroups = (pl->num_qtiles + qt - 1) / qt;     // work items per row chunk
+    pl->q_pad = num_qgroups * qt * n_tile;                           // an odd last group is padded with an empty tile
     // ---- candidate capacity and phase growth: expected survivors per phase ~ k * growth <= cap / 4
     uint32_t cap = pow2_ceil(16u * k);
     if (cap < 512u) cap = 512u;
@@ -1088,7 +1178,7 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
         for (uint32_t c = 1; c <= cmax; ++c) {
             const uint32_t tpc = (units + c - 1) / c;
             const uint32_t chunks = (units + tpc - 1) / tpc;
-            const unsigned long long items = (unsigned long long)chunks * pl->num_qtiles;
+            const unsigned long long items = (unsigned long long)chunks * num_qgroups;
             const unsigned long long waves = (items + workers - 1) / workers;
             const double cost = (double)waves * ((double)tpc + 1.5);
             if (cost < best_cost) {
@@ -1098,7 +1188,7 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
         }
         P.tiles_per_chunk = best_tpc;
         P.num_chunks = units ? (units + best_tpc - 1) / best_tpc : 0;
-        const unsigned long long items = (unsigned long long)P.num_chunks * pl->num_qtiles;
+        const unsigned long long items = (unsigned long long)P.num_chunks * num_qgroups;
         const uint32_t busy = (uint32_t)(items < (unsigned long long)workers ? items : (unsigned long long)workers);
         P.grid = pair ? 2u * busy : busy;
     }
@@ -1172,6 +1262,7 @@ cudaError_t run_mma_top_n(const MmaPlan& pl, const uint64_t* d_hashes, unsigned 
             sp.group_kb = pl.group_kb;
             sp.ring_per_issuer = pl.ring_per_issuer;
             sp.pair = pl.pair;
+            sp.qt_per_item = pl.qt;
             sp.trace = nullptr;
             const char* trace_path = dev_knob("NPS_MMA_TRACE");
             const char* trace_phase = dev_knob("NPS_MMA_TRACE_PHASE");

@@ -67,6 +67,7 @@ struct MmaScanParams {
     uint32_t a_stages, p_stages;
     uint32_t group_kb, ring_per_issuer;   // A ring: 2 x ring_per_issuer groups of group_kb K-block stages
     uint32_t pair;             // CTA pairs (cta_group::2): phase_tiles counts row tiles, chunks count tile PAIRS
+    uint32_t qt_per_item;      // query tiles per work item (2: pairs only — every expanded row tile meets two query tiles)
     unsigned long long* trace; // development only: per-role event timestamps of CTA 0
     uint32_t debug;            // development only: 1 = no epilogue filter, 2 = no expansion, 4 = no MMA
 };
@@ -77,18 +78,18 @@ struct MmaSmem {
 };
 __host__ __device__ inline uint32_t mma_kblocks(uint32_t words) { return (words + 3) / 4; }
 __host__ __device__ inline MmaSmem mma_smem_layout(uint32_t words, uint32_t n_tile, uint32_t a_stages,
-                                                   uint32_t p_stages, uint32_t pair = 0) {
+                                                   uint32_t p_stages, uint32_t pair = 0, uint32_t qt = 1) {
     MmaSmem s;
     uint32_t off = 0;
     s.b_off = off;
     const uint32_t b_rows = pair ? n_tile / 2 : n_tile;   // a CTA of a pair holds half of the query tile
-    off += mma_kblocks(words) * b_rows * kMmaKBlockBytes;
+    off += qt * mma_kblocks(words) * b_rows * kMmaKBlockBytes;   // qt query tiles resident per work item
     s.a_off = off;
     off += a_stages * kMmaAStageBytes;
     s.athr_off = off;   // threshold operand tiles (no-swizzle K-major, one K = 64 slice): A = 4.0 everywhere,
     off += kMmaTileRows * 32;
     s.bthr_off = off;   // B row n = -(threshold of query n) / 4 spelled in E2M1 elements; a second tile
-    off += b_rows * 32 * (words > kMmaThrOneSlice ? 2u : 1u);   // (second slice) for wide signatures
+    off += qt * b_rows * 32 * (words > kMmaThrOneSlice ? 2u : 1u);   // (second slice) for wide signatures
     s.p_off = off;
     s.p_stride = (kMmaTileRows * words * 8 + 127u) & ~127u;
     off += p_stages * s.p_stride;
@@ -96,7 +97,7 @@ __host__ __device__ inline MmaSmem mma_smem_layout(uint32_t words, uint32_t n_ti
     off += kMmaEpiWarps * (kMmaHitsPerWarp + 1) * 8;   // (accumulator bits, position code) + 1 overflow slot
     s.hitq_off = off;
     s.thr_off = off;   // per epilogue warp: thresholds of its column groups
-    off += kMmaEpiWarps * 64u * 4u;
+    off += qt * kMmaEpiWarps * 64u * 4u;
     s.wcnt_off = off;
     off += kMmaEpiWarps * 4;
     off = (off + 7u) & ~7u;
@@ -137,6 +138,7 @@ struct MmaPhase {
 struct MmaPlan {
     uint32_t n_tile, num_qtiles, q_pad, cap, growth, a_stages, p_stages, group_kb, ring_per_issuer, smem, sort_cap, num_phases;
     uint32_t pair;             // 1: CTA pairs (cta_group::2, M = 256); chunks of a phase then count tile pairs
+    uint32_t qt;               // query tiles per work item (1 or 2)
     MmaPhase phase[kMmaMaxPhases];
     // workspace carve-up (bytes from the workspace base)
     size_t off_flag, off_cnt, off_thrT, off_thrK, off_best, off_cand, total;

@@ -15,6 +15,12 @@ _lib.set_scan_path(_lib.SCAN_MMA)
 configs = [
     ("single", {"NPS_MMA_PAIR": "0"}),
     ("pair", {"NPS_MMA_PAIR": "1"}),
+    ("single groups 1,3", {"NPS_MMA_PAIR": "0", "NPS_MMA_GROUPS": "1,3"}),
+    ("single groups 1,3 no-mma", {"NPS_MMA_PAIR": "0", "NPS_MMA_GROUPS": "1,3", "NPS_MMA_DEBUG": "4"}),
+    ("pair groups 1,3 qt1", {"NPS_MMA_PAIR": "1", "NPS_MMA_QT1": "1", "NPS_MMA_GROUPS": "1,3"}),
+    ("pair groups 1,4 qt1", {"NPS_MMA_PAIR": "1", "NPS_MMA_QT1": "1", "NPS_MMA_GROUPS": "1,4"}),
+    ("pair one-qtile", {"NPS_MMA_PAIR": "1", "NPS_MMA_QT1": "1"}),
+    ("pair no-mma(4) qt2", {"NPS_MMA_PAIR": "1", "NPS_MMA_DEBUG": "4"}),
     ("pair pstages 2", {"NPS_MMA_PAIR": "1", "NPS_MMA_PSTAGES": "2"}),
     ("pair pstages 4", {"NPS_MMA_PAIR": "1", "NPS_MMA_PSTAGES": "4"}),
     ("pair pstages 4 no-mma", {"NPS_MMA_PAIR": "1", "NPS_MMA_PSTAGES": "4", "NPS_MMA_DEBUG": "4"}),
@@ -30,7 +36,7 @@ configs = [
     ("single no-mma(4)", {"NPS_MMA_PAIR": "0", "NPS_MMA_DEBUG": "4"}),
     ("single no-epilogue(8)", {"NPS_MMA_PAIR": "0", "NPS_MMA_DEBUG": "8"}),
 ]
-knobs = ("NPS_MMA_PAIR", "NPS_MMA_GROUPS", "NPS_MMA_DEBUG", "NPS_MMA_PSTAGES")
+knobs = ("NPS_MMA_PAIR", "NPS_MMA_GROUPS", "NPS_MMA_DEBUG", "NPS_MMA_PSTAGES", "NPS_MMA_QT1")
 for name, env in configs:
     for kk in knobs:
         os.environ.pop(kk, None)
@@ -51,7 +57,7 @@ for name, env in configs:
         print("%-28s total %.3f ms  phases %s  smem %d a_stages %d" % (name, tot, [round(m, 3) for _, m in ph], plan["smem_bytes"], plan["a_stages"]), flush=True)
         if "--check" in sys.argv and "DEBUG" not in "".join(env):
             got = np_sims.hamming_top_n(H, Qs, k)
-            os.environ["NPS_MMA_PAIR"] = "0"; os.environ.pop("NPS_MMA_PSTAGES", None); os.environ.pop("NPS_MMA_GROUPS", None)
+            os.environ["NPS_MMA_PAIR"] = "0"; os.environ.pop("NPS_MMA_PSTAGES", None); os.environ.pop("NPS_MMA_GROUPS", None); os.environ.pop("NPS_MMA_QT1", None)
             want = np_sims.hamming_top_n(H, Qs, k)
             print("    equal to single:", bool(torch.equal(got.view(torch.int64), want.view(torch.int64))), flush=True)
     except Exception as e:
