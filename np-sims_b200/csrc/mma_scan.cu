@@ -1126,6 +1126,14 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
     uint32_t growth = cap / (4u * k);
     if (growth > 8u) growth = 8u;
     if (growth < 2u) growth = 2u;
+    // Small batches (a 10 000-query batch split over 8 GPUs leaves 6 query tiles per rank): every phase costs
+    // ~25 us of launch + prologue + select whatever its size, and the epilogue has slack, so fewer, coarser
+    // phases win — twice the candidate capacity (a denser first sample) and two doubling phases at the end
+    // instead of three (measured, 400k x 640 bit, profiles/r02_phase_sweep.txt: 1250 queries 0.396 -> 0.354 ms,
+    // 2500 queries 0.576 -> 0.535 ms; growth 16 is 3 % faster still but lets twice as much of the unsampled
+    // tail of a sorted table through; from 10 000 queries on the finer schedule is the faster one).
+    const bool small_batch = pl->num_qtiles <= 12 && k <= 32;
+    if (small_batch) cap = 1024u;
     if (const char* e = dev_knob("NPS_MMA_CAP")) cap = (uint32_t)atoi(e);          // development
     if (const char* e = dev_knob("NPS_MMA_GROWTH")) growth = (uint32_t)atoi(e);    // development
     pl->cap = cap;
@@ -1147,7 +1155,7 @@ bool mma_plan(unsigned long long N, uint32_t W, uint32_t Q, uint32_t k, int sm_c
     uint32_t np = 0;
     exps[np++] = e0;
     for (uint32_t e = e0; e > 0;) {
-        uint32_t late = 3;   // number of final phases that only double
+        uint32_t late = small_batch ? 2u : 3u;   // number of final phases that only double
         if (const char* ev = dev_knob("NPS_MMA_LATE")) late = (uint32_t)atoi(ev);   // development
         const uint32_t step = e <= late ? 1u : (e - late < gshift ? e - late : gshift);
         e -= step;
