@@ -152,8 +152,12 @@ __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t
             }
             const uint32_t all = __shfl_sync(0xffffffffu, incl, 31);
             if (all) {   // warp-uniform
-                uint32_t basepos = 0;
-                if (lane == 31) basepos = atomicAdd(p.fix_count, all);
+                // Saturating: once the list has overflowed (count > capacity: the gated float64 launch redoes the whole
+                // call) nothing more is added, so the 32-bit counter cannot wrap on degenerate multi-million-row
+                // input (every pair unsure) and hide the overflow.
+                uint32_t basepos = p.fix_cap;
+                if (lane == 31 && *reinterpret_cast<volatile unsigned int*>(p.fix_count) <= p.fix_cap)
+                    basepos = atomicAdd(p.fix_count, all);
                 basepos = __shfl_sync(0xffffffffu, basepos, 31);
                 uint32_t pos = basepos + incl - mine;
 #pragma unroll
