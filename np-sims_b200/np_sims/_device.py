@@ -160,7 +160,9 @@ def u64_table(x, name: str, ndim: int | None = None):
     if ndim is not None and arr.ndim != ndim:
         raise ValueError(f"{name}: expected {ndim} dimensions, got {arr.ndim}")
     if cached is not None:
-        return cached, True
+        if cached.device.index == t.cuda.current_device():
+            return cached, True
+        return cached.to(t.device("cuda", t.cuda.current_device())), True   # resident copy lives on another GPU: not cached
     arr = np.ascontiguousarray(arr)
     dev = t.from_numpy(arr.view(np.int64)).cuda()
     if isinstance(x, DeviceArray):

@@ -26,7 +26,8 @@ def time_call(fn, reps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=16_000_000)
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_c5_sweep.json"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r02_c5_sweep.json"))
+    ap.add_argument("--table", default=None, help="also write the latency table (text) here")
     ap.add_argument("--force", default="auto", choices=["auto", "popc", "mma", "both"])
     args = ap.parse_args()
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
@@ -39,8 +40,6 @@ def main():
         H = torch.randint(-2**63, 2**63 - 1, (args.rows, w), dtype=torch.int64, device=dev, generator=g)
         for k in (1, 10, 100, 1000):
             for batch in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096):
-                if k == 1000 and batch > 1024:
-                    continue
                 Q = torch.randint(-2**63, 2**63 - 1, (batch, w), dtype=torch.int64, device=dev, generator=g)
                 paths = {"auto": [_lib.SCAN_AUTO], "popc": [_lib.SCAN_POPC], "mma": [_lib.SCAN_MMA],
                          "both": [_lib.SCAN_POPC, _lib.SCAN_MMA]}[args.force]
@@ -50,7 +49,8 @@ def main():
                     prev = _lib.set_scan_path(path)
                     try:
                         med, best = time_call(lambda: np_sims.hamming_top_n(H, Q, k), 5 if batch * args.rows * w < 4e12 else 2)
-                        used = "mma" if _lib.raw("nps_last_scan_path")() == _lib.SCAN_MMA else "popc"
+                        used = "mma" if _lib.raw("nps_last_scan_path")() == _lib.SCAN_MMA else (
+                            "hist" if _lib.last_scan_plan()["cap"] == 0 else "popc")
                     finally:
                         _lib.set_scan_path(prev)
                     table_gb = args.rows * w * 8 / 1e9
@@ -62,6 +62,19 @@ def main():
                     print(json.dumps(pt), flush=True)
         del H
     json.dump(out, open(args.out, "w"), indent=0)
+    if args.table:
+        cols = (1, 4, 16, 64, 256, 1024, 4096)
+        with open(args.table, "w") as f:
+            f.write(f"# C5 sweep, {args.rows // 1_000_000}M-row table, one B200, hamming_top_n call latency in ms (median of 5), "
+                    "h = K2H table stream + counting select, p = K2 XOR+POPC lists, m = tcgen05 phases\n")
+            f.write("bits    k | " + " | ".join(f"{c:7d}" for c in cols) + "\n")
+            for bits in (64, 128, 256, 512, 640, 1024, 2048):
+                for k in (1, 10, 100, 1000):
+                    cells = []
+                    for c in cols:
+                        pt = [p for p in out["points"] if p["bits"] == bits and p["k"] == k and p["batch"] == c]
+                        cells.append(f"{pt[0]['ms']:6.2f}{pt[0]['path'][0]}" if pt else "      -")
+                    f.write(f"{bits:5d} {k:4d} | " + " | ".join(cells) + "\n")
 
 
 if __name__ == "__main__":
