@@ -576,8 +576,21 @@ __global__ void __launch_bounds__(256) project_fix_kernel(const unsigned long lo
         const uint32_t col = (uint32_t)(code & 0xFFFFu);
         const float* x = X + row * D;
         const double* w = W + (size_t)col * D;
-        double s = 0.0;
-        for (uint32_t k = lane; k < D; k += 32) s = fma((double)x[k], w[k], s);
+        // D % 4 == 0 on this path: 16-byte loads, four elements per lane and step, the loads of a row issued
+        // together (one warp per pair is bound by load latency: scalar lane-strided loads took 0.8 ns per pair
+        // at 32 % of the DRAM peak, profiles/r02_ncu_k1t_k2t.txt)
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+        for (uint32_t k = lane * 4u; k < D; k += 128u) {
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(x + k));
+            const double2 wa = __ldg(reinterpret_cast<const double2*>(w + k));
+            const double2 wb = __ldg(reinterpret_cast<const double2*>(w + k + 2));
+            s0 = fma((double)xv.x, wa.x, s0);
+            s1 = fma((double)xv.y, wa.y, s1);
+            s0 = fma((double)xv.z, wb.x, s0);
+            s1 = fma((double)xv.w, wb.y, s1);
+        }
+        double s = s0 + s1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) {
