@@ -30,8 +30,9 @@
 // An accumulator is trusted when |C1 + C2| >= eps |x_i| max_j |w_j|,  eps = (8 + D/4) * 2^-22
 // (2.0e-5 at D = 300: 0.03 % of all pairs; 4.8e-5 at D = 768: 0.1 %).  Every other (row,
 // projection) pair — and every row whose norm is not a comfortable float32 (zero, < 1e-18,
-// > 1e18, inf, NaN) — goes to a fix-up list and is recomputed in float64 by project_fix_kernel,
-// which sets the bit the way the reference would.  If the list overflows (degenerate input), a
+// > 1e18, inf, NaN) — is recomputed in float64 and its bit set the way the reference would: by the
+// CTA's own fixer warps while the tile's rows are still in L2 (BF16 kernel: the usual handful per warp
+// and item, through a shared-memory ring), or through a global fix-up list and project_fix_kernel.  If the list overflows (degenerate input), a
 // gated launch of the float64 kernel redoes the whole call on the device.  Signatures therefore
 // agree with the float64 path bit for bit (up to float64 summation order at |x.w| ~ 1e-16, as for
 // project_f64.cu); the flipped-bit rate BEFORE fix-up is what the tests report as the tolerance.
@@ -59,6 +60,37 @@ struct ProjTcParams {
     uint32_t D, B, num_ntiles, stages, fix_cap;
     float tol_scale;            // eps * max_j |w_j|
     unsigned long long num_mtiles;
+    const float* X;             // [N, D] the rows again, for the float64 recomputation in the epilogue
+    const double* W64;          // [B, D]
+};
+
+// float64 x_row . w_col by one warp, every lane gets the sum.  D % 4 == 0 on this path: 16-byte loads,
+// four elements per lane and step, the loads of a row issued together.
+__device__ __forceinline__ double fix_dot(const float* __restrict__ x, const double* __restrict__ w, uint32_t D,
+                                          int lane) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+    for (uint32_t k = lane * 4u; k < D; k += 128u) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + k));
+        const double2 wa = __ldg(reinterpret_cast<const double2*>(w + k));
+        const double2 wb = __ldg(reinterpret_cast<const double2*>(w + k + 2));
+        s0 = fma((double)xv.x, wa.x, s0);
+        s1 = fma((double)xv.y, wa.y, s1);
+        s0 = fma((double)xv.z, wb.x, s0);
+        s1 = fma((double)xv.w, wb.y, s1);
+    }
+    double s = s0 + s1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+// Unsure entries on their way from the epilogue warps to the fixer warps of the same CTA: one
+// single-producer single-consumer ring per epilogue warp (quarter).  The producer never blocks: what does not
+// fit goes to the global fix-up list instead.
+constexpr uint32_t kPtFixQ = 128;
+struct FixQueue {
+    uint32_t head[4], tail[4], done[4], pad[4];
+    unsigned long long ent[4][kPtFixQ];   // row << 16 | projection
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t c0, uint32_t c1,
@@ -86,8 +118,8 @@ __device__ __forceinline__ uint32_t tf32_low_part(uint32_t x) {
     return rn_tf32(__uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u));
 }
 
-// Epilogue shared by both operand encodings: signs of C1 + C2 -> uint64 words, uncertain entries ->
-// fix-up list (one atomic per warp and item).  Accumulator buffer b holds C1 at columns [2 NT b, +NT)
+// Epilogue shared by both operand encodings: signs of C1 + C2 -> uint64 words; uncertain entries go to
+// the CTA's fixer warps (fq, BF16 kernel) or to the global fix-up list (one atomic per warp and item).  Accumulator buffer b holds C1 at columns [2 NT b, +NT)
 // and C2 right behind it.
 // norm_s: null -> |x_i| comes from p.norms (row_norm_kernel); else the splitter warps left it in shared
 // memory, kPtNormBufs buffers of 128 floats indexed by the item count (BF16 kernel).
@@ -95,12 +127,12 @@ constexpr uint32_t kPtNormBufs = 8;   // splitters run at most 2 + stages items 
 template <uint32_t NT>
 __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t tmem_base, uint64_t* acc_full,
                                                  uint64_t* acc_empty, int warp, int lane, unsigned long long total,
-                                                 const float* norm_s = nullptr) {
+                                                 const float* norm_s = nullptr, FixQueue* fq = nullptr) {
         const uint32_t quarter = warp & 3u;
         const uint32_t r_in_tile = quarter * 32u + lane;
         const uint32_t words_per_row = p.B / 64u;
         constexpr uint32_t G = NT / 32u;       // 32-column groups per item
-        uint32_t t_idx = 0;
+        uint32_t t_idx = 0, q_head = 0;
         for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx) {
             const unsigned long long mt = item / p.num_ntiles;
             const uint32_t nt = (uint32_t)(item - mt * p.num_ntiles);
@@ -118,16 +150,19 @@ __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t
             uint32_t sign_m[G], unsure_m[G];
 #pragma unroll
             for (uint32_t g = 0; g < G; ++g) {
-                uint32_t v1[32], v2[32];
-                tmem_ld32(t_addr + g * 32u, v1);
-                tmem_ld32(t_addr + NT + g * 32u, v2);
-                tmem_ld_wait();
                 uint32_t bits = 0, unsure = 0;      // per column: sign, |acc| below the tolerance
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float a = __uint_as_float(v1[j]) + __uint_as_float(v2[j]);
-                    bits |= (a >= 0.f ? 1u : 0u) << j;
-                    unsure |= (fabsf(a) < tol ? 1u : 0u) << j;
+                for (uint32_t h = 0; h < 2; ++h) {  // 16 columns at a time: 32 live registers, not 64
+                    uint32_t v1[16], v2[16];
+                    tmem_ld16_at<0>(t_addr + g * 32u + h * 16u, v1);
+                    tmem_ld16_at<0>(t_addr + NT + g * 32u + h * 16u, v2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float a = __uint_as_float(v1[j]) + __uint_as_float(v2[j]);
+                        bits |= (a >= 0.f ? 1u : 0u) << (h * 16u + j);
+                        unsure |= (fabsf(a) < tol ? 1u : 0u) << (h * 16u + j);
+                    }
                 }
                 sign_m[g] = bits;
                 unsure_m[g] = !valid ? 0u : (tame ? unsure : 0xFFFFFFFFu);
@@ -135,12 +170,6 @@ __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);   // accumulator free before the global traffic below
-            if (valid) {
-#pragma unroll
-                for (uint32_t g = 0; g < G; g += 2)
-                    p.out[row * words_per_row + (nt * NT + g * 32u) / 64u] =
-                        (uint64_t)sign_m[g] | ((uint64_t)sign_m[g + 1] << 32);
-            }
             uint32_t mine = 0;
 #pragma unroll
             for (uint32_t g = 0; g < G; ++g) mine += __popc(unsure_m[g]);
@@ -150,8 +179,33 @@ __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t
                 const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += up;
             }
-            const uint32_t all = __shfl_sync(0xffffffffu, incl, 31);
-            if (all) {   // warp-uniform
+            uint32_t all = __shfl_sync(0xffffffffu, incl, 31);
+            if (valid) {
+#pragma unroll
+                for (uint32_t g = 0; g < G; g += 2)
+                    p.out[row * words_per_row + (nt * NT + g * 32u) / 64u] =
+                        (uint64_t)sign_m[g] | ((uint64_t)sign_m[g + 1] << 32);
+            }
+            if (all != 0u && fq != nullptr) {   // warp-uniform
+                // The usual case (0.1 % of the pairs: a handful per warp and item): hand them to this quarter's fixer
+                // warp, which recomputes them in float64 while the tile's rows are still in L2 and patches the
+                // words stored above.  (A separate pass over a list re-read every such row from DRAM: 40 GB at C3.)
+                const uint32_t tail = *reinterpret_cast<volatile uint32_t*>(&fq->tail[quarter]);
+                if (q_head + all - tail <= kPtFixQ) {
+                    uint32_t pos = q_head + incl - mine;
+#pragma unroll
+                    for (uint32_t g = 0; g < G; ++g)
+                        for (uint32_t m = unsure_m[g]; m; m &= m - 1u, ++pos)
+                            fq->ent[quarter][pos % kPtFixQ] =
+                                (row << 16) | (unsigned long long)(nt * NT + g * 32u + (__ffs(m) - 1));
+                    __threadfence_block();     // words and entries before the new head
+                    __syncwarp();
+                    q_head += all;
+                    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&fq->head[quarter]) = q_head;
+                    all = 0;
+                }
+            }
+            if (all) {   // no fixer warps (TF32 kernel), ring full, degenerate rows: the list and project_fix_kernel
                 // Saturating: once the list has overflowed (count > capacity: the gated float64 launch redoes the whole
                 // call) nothing more is added, so the 32-bit counter cannot wrap on degenerate multi-million-row
                 // input (every pair unsure) and hide the overflow.
@@ -167,6 +221,93 @@ __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t
                             p.fix[pos] = (row << 16) | (unsigned long long)(nt * NT + g * 32u + (__ffs(m) - 1));
             }
         }
+        if (fq != nullptr && lane == 0) *reinterpret_cast<volatile uint32_t*>(&fq->done[quarter]) = 1u;
+}
+
+// Fixer warp f of kPbFixers: drains rings f, f + kPbFixers, ... until their epilogue warps are done.
+constexpr uint32_t kPbFixers = 4;
+// Entries a fixer warp recomputes together.  C3 on one B200: no fixer warps (list + project_fix_kernel only) 68.4-69.8 ms,
+// 1 -> 65.2-65.5 (28 % of the entries overflow the rings to the list), 2 -> 65.1-65.3 (none overflow), 4 -> 66.4-66.6.
+constexpr uint32_t kPbFixBatch = 2;
+__device__ __forceinline__ void project_fixer(const ProjTcParams& p, FixQueue* fq, uint32_t f, int lane) {
+    constexpr int kRings = 4 / kPbFixers;
+    uint32_t tail[kRings] = {};
+    uint32_t live = (1u << kRings) - 1u;
+    while (live) {
+        bool idle = true;
+#pragma unroll
+        for (int h = 0; h < kRings; ++h) {
+            if (!(live >> h & 1u)) continue;
+            const uint32_t q = f + kPbFixers * h;
+            uint32_t done = 0, head = 0;
+            if (lane == 0) {
+                done = *reinterpret_cast<volatile uint32_t*>(&fq->done[q]);
+                __threadfence_block();
+                head = *reinterpret_cast<volatile uint32_t*>(&fq->head[q]);
+            }
+            done = __shfl_sync(0xffffffffu, done, 0);
+            head = __shfl_sync(0xffffffffu, head, 0);
+            if (head == tail[h]) {
+                if (done) live &= ~(1u << h);
+                continue;
+            }
+            idle = false;
+            __threadfence_block();
+            while (tail[h] != head) {
+                // kPbFixBatch entries at a time: one warp on one entry is a chain of L2 round trips and does not keep
+                // up with the epilogue; the loads of a batch overlap.  A short batch repeats its first entry (unused).
+                const uint32_t n = min(head - tail[h], kPbFixBatch);
+                unsigned long long code[kPbFixBatch];
+                const float* x[kPbFixBatch];
+                const double* w[kPbFixBatch];
+#pragma unroll
+                for (uint32_t e = 0; e < kPbFixBatch; ++e) {
+                    code[e] = fq->ent[q][(tail[h] + (e < n ? e : 0u)) % kPtFixQ];
+                    x[e] = p.X + (code[e] >> 16) * p.D;
+                    w[e] = p.W64 + (size_t)(code[e] & 0xFFFFu) * p.D;
+                }
+                double s0[kPbFixBatch] = {}, s1[kPbFixBatch] = {};
+#pragma unroll 2
+                for (uint32_t k = lane * 4u; k < p.D; k += 128u) {
+#pragma unroll
+                    for (uint32_t e = 0; e < kPbFixBatch; ++e) {
+                        const float4 xv = __ldg(reinterpret_cast<const float4*>(x[e] + k));
+                        const double2 wa = __ldg(reinterpret_cast<const double2*>(w[e] + k));
+                        const double2 wb = __ldg(reinterpret_cast<const double2*>(w[e] + k + 2));
+                        s0[e] = fma((double)xv.x, wa.x, s0[e]);
+                        s1[e] = fma((double)xv.y, wa.y, s1[e]);
+                        s0[e] = fma((double)xv.z, wb.x, s0[e]);
+                        s1[e] = fma((double)xv.w, wb.y, s1[e]);
+                    }
+                }
+                double mine = 0.0;      // lane e ends up with the sum of entry e
+#pragma unroll
+                for (uint32_t e = 0; e < kPbFixBatch; ++e) {
+                    double t = s0[e] + s1[e];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    if (lane == (int)e) mine = t;
+                }
+                unsigned long long mycode = code[0];
+#pragma unroll
+                for (uint32_t e = 1; e < kPbFixBatch; ++e)
+                    if (lane == (int)e) mycode = code[e];
+                if ((uint32_t)lane < n) {
+                    const unsigned long long row = mycode >> 16;
+                    const uint32_t col = (uint32_t)(mycode & 0xFFFFu);
+                    unsigned long long* word =
+                        reinterpret_cast<unsigned long long*>(p.out) + row * (p.B / 64u) + col / 64u;
+                    const unsigned long long mask = 1ull << (col & 63u);
+                    if (mine >= 0.0) atomicOr(word, mask);
+                    else atomicAnd(word, ~mask);
+                }
+                tail[h] += n;
+                __syncwarp();
+                if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&fq->tail[q]) = tail[h];
+            }
+        }
+        if (idle) __nanosleep(500);
+    }
 }
 
 // Stage layout: [xh tile 16 KB][xl tile 16 KB][wh tile NT x 128 B][wl tile NT x 128 B]
@@ -334,10 +475,10 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& h, uint
 // look-ahead) and operands (S x [x0 16 KB | x1 16 KB | w0 | w1]).  Two producer threads (X and W) so that
 // neither waits on the other's ring.
 constexpr uint32_t kPbRawSlots = 2;
-constexpr int kPbThreads = 11 * 32;     // X producer, MMA issuer, 4 epilogue warps, 4 splitter warps, W producer
+constexpr int kPbThreads = (11 + kPbFixers) * 32;   // X producer, MMA issuer, 4 epilogue, 4 splitter warps, W producer, fixer warps
 
 template <uint32_t NT>
-__global__ void __launch_bounds__(kPbThreads, 1)
+__global__ void __launch_bounds__(kPbThreads, 1)   // 4 warps per sub-partition: 128 registers
 project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                     const ProjTcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -360,8 +501,10 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     uint64_t* acc_empty = acc_full + 2;     // [2]
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* norm_s = reinterpret_cast<float*>(tmem_ptr_s + 4);   // [kPtNormBufs][128]: |x_i| from the splitters
+    FixQueue* fq = reinterpret_cast<FixQueue*>(norm_s + kPtNormBufs * kPtTileRows);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 16) fq->head[tid] = 0u;   // head, tail, done, pad
     if (tid == 0) {
         for (uint32_t s = 0; s < R; ++s) {
             mbar_init(&raw_full[s], 1);
@@ -459,6 +602,8 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 }
             }
         }
+    } else if (warp >= 11) {
+        project_fixer(p, fq, (uint32_t)warp - 11u, lane);
     } else if (warp >= 6) {
         // ===== splitters: thread = row.  Output chunk j (8 bf16 = floats 8j .. 8j+7 of the K-block) comes from
         // 16-byte chunks 2(j&3), 2(j&3)+1 of raw box j>>2; every access is the row's 128-byte line with the
@@ -507,7 +652,7 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             }
         }
     } else {
-        project_epilogue<NT>(p, tmem_base, acc_full, acc_empty, warp, lane, total, norm_s);
+        project_epilogue<NT>(p, tmem_base, acc_full, acc_empty, warp, lane, total, norm_s, fq);
     }
     tc_fence_before();
     __syncthreads();
@@ -576,23 +721,7 @@ __global__ void __launch_bounds__(256) project_fix_kernel(const unsigned long lo
         const uint32_t col = (uint32_t)(code & 0xFFFFu);
         const float* x = X + row * D;
         const double* w = W + (size_t)col * D;
-        // D % 4 == 0 on this path: 16-byte loads, four elements per lane and step, the loads of a row issued
-        // together (one warp per pair is bound by load latency: scalar lane-strided loads took 0.8 ns per pair
-        // at 32 % of the DRAM peak, profiles/r02_ncu_k1t_k2t.txt)
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll 4
-        for (uint32_t k = lane * 4u; k < D; k += 128u) {
-            const float4 xv = __ldg(reinterpret_cast<const float4*>(x + k));
-            const double2 wa = __ldg(reinterpret_cast<const double2*>(w + k));
-            const double2 wb = __ldg(reinterpret_cast<const double2*>(w + k + 2));
-            s0 = fma((double)xv.x, wa.x, s0);
-            s1 = fma((double)xv.y, wa.y, s1);
-            s0 = fma((double)xv.z, wb.x, s0);
-            s1 = fma((double)xv.w, wb.y, s1);
-        }
-        double s = s0 + s1;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const double s = fix_dot(x, w, D, lane);
         if (lane == 0) {
             unsigned long long* word = out + row * (B / 64u) + col / 64u;
             const unsigned long long mask = 1ull << (col & 63u);
@@ -680,6 +809,8 @@ cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, 
     p.N = N;
     p.D = D;
     p.B = B;
+    p.X = X;
+    p.W64 = W64;
     const uint32_t n_tile = (B % 128 == 0) ? 128 : 64;
     p.num_ntiles = B / n_tile;
     p.num_mtiles = (N + kPtTileRows - 1) / kPtTileRows;
@@ -688,7 +819,7 @@ cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, 
     p.tol_scale = ((use_bf16 ? 52.0f : 8.0f) + 0.25f * (float)D) / 4194304.0f * w_norm_max;
     // TF32: stages of [xh | xl | wh | wl]; BF16: a raw-X ring of kPbRawSlots x 32 KB + operand slots [x0 | x1 | w0 | w1]
     const uint32_t stage_bytes = 2u * kPtAStage + 2u * n_tile * 128u;
-    const uint32_t fixed = use_bf16 ? kPbRawSlots * 2u * kPtAStage + kPtNormBufs * kPtTileRows * 4u : 0u;
+    const uint32_t fixed = use_bf16 ? kPbRawSlots * 2u * kPtAStage + kPtNormBufs * kPtTileRows * 4u + (uint32_t)sizeof(FixQueue) : 0u;
     uint32_t stages = (uint32_t)((smem_optin - 2048 - (int)fixed) / (int)stage_bytes);
     if (stages > 4) stages = 4;
     if (stages < 2) return cudaErrorInvalidValue;
