@@ -39,6 +39,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "project.cuh"
@@ -87,7 +88,10 @@ __device__ __forceinline__ double fix_dot(const float* __restrict__ x, const dou
 // Unsure entries on their way from the epilogue warps to the fixer warps of the same CTA: one
 // single-producer single-consumer ring per epilogue warp (quarter).  The producer never blocks: what does not
 // fit goes to the global fix-up list instead.
-constexpr uint32_t kPtFixQ = 128;
+#ifndef NPS_PT_FIXQ
+#define NPS_PT_FIXQ 128
+#endif
+constexpr uint32_t kPtFixQ = NPS_PT_FIXQ;
 struct FixQueue {
     uint32_t head[4], tail[4], done[4], pad[4];
     unsigned long long ent[4][kPtFixQ];   // row << 16 | projection
@@ -121,13 +125,15 @@ __device__ __forceinline__ uint32_t tf32_low_part(uint32_t x) {
 // Epilogue shared by both operand encodings: signs of C1 + C2 -> uint64 words; uncertain entries go to
 // the CTA's fixer warps (fq, BF16 kernel) or to the global fix-up list (one atomic per warp and item).  Accumulator buffer b holds C1 at columns [2 NT b, +NT)
 // and C2 right behind it.
-// norm_s: null -> |x_i| comes from p.norms (row_norm_kernel); else the splitter warps left it in shared
-// memory, kPtNormBufs buffers of 128 floats indexed by the item count (BF16 kernel).
+// norm_s: null -> |x_i| comes from p.norms (row_norm_kernel); else the splitter groups left their sums of
+// squares in shared memory, kPtNormBufs buffers of [norm_parts <= 2][128] floats indexed by the item count
+// (BF16 kernel).
 constexpr uint32_t kPtNormBufs = 8;   // splitters run at most 2 + stages items ahead of the epilogue
-template <uint32_t NT>
+template <uint32_t NT, uint32_t NBUF = 2, bool kRelaxed = false>
 __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t tmem_base, uint64_t* acc_full,
                                                  uint64_t* acc_empty, int warp, int lane, unsigned long long total,
-                                                 const float* norm_s = nullptr, FixQueue* fq = nullptr) {
+                                                 const float* norm_s = nullptr, FixQueue* fq = nullptr,
+                                                 uint32_t norm_parts = 1) {
         const uint32_t quarter = warp & 3u;
         const uint32_t r_in_tile = quarter * 32u + lane;
         const uint32_t words_per_row = p.B / 64u;
@@ -136,14 +142,20 @@ __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t
         for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx) {
             const unsigned long long mt = item / p.num_ntiles;
             const uint32_t nt = (uint32_t)(item - mt * p.num_ntiles);
-            const uint32_t buf = t_idx & 1u;
+            const uint32_t buf = t_idx % NBUF;
             const unsigned long long row = mt * kPtTileRows + r_in_tile;
             const bool valid = row < p.N;
             float norm = (valid && norm_s == nullptr) ? __ldg(p.norms + row) : 1.f;
-            mbar_wait(&acc_full[buf], (t_idx >> 1) & 1u);
+            if (kRelaxed) mbar_wait_relaxed(&acc_full[buf], (t_idx / NBUF) & 1u);   // sleeps in hardware, no polling
+            else mbar_wait(&acc_full[buf], (t_idx / NBUF) & 1u);
             tc_fence_after();
-            if (valid && norm_s != nullptr)      // written before the splitters' last split_done of the item
-                norm = reinterpret_cast<const volatile float*>(norm_s)[(t_idx % kPtNormBufs) * kPtTileRows + r_in_tile];
+            if (valid && norm_s != nullptr) {    // written before the splitters' last split_done of the item
+                // norm_parts: 1 = one splitter group; 2 = two, both saw part of the row; 3 = two groups and one K-block
+                // per item: the group of this item's only K-block is t_idx & 1
+                const volatile float* ns = norm_s + (t_idx % kPtNormBufs) * 2u * kPtTileRows + r_in_tile;
+                norm = sqrtf(norm_parts == 3u ? ns[(t_idx & 1u) * kPtTileRows]
+                                              : ns[0] + (norm_parts == 2u ? ns[kPtTileRows] : 0.f)) * 1.001f;
+            }
             const bool tame = norm >= 1e-18f && norm <= 1e18f;     // false for 0, tiny, huge, inf, NaN
             const float tol = p.tol_scale * norm;
             const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * (2u * NT);
@@ -224,13 +236,16 @@ __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t
         if (fq != nullptr && lane == 0) *reinterpret_cast<volatile uint32_t*>(&fq->done[quarter]) = 1u;
 }
 
-// Fixer warp f of kPbFixers: drains rings f, f + kPbFixers, ... until their epilogue warps are done.
-constexpr uint32_t kPbFixers = 4;
+// Fixer warp f of kFixers: drains rings f, f + kFixers, ... until their epilogue warps are done.
 // Entries a fixer warp recomputes together.  C3 on one B200: no fixer warps (list + project_fix_kernel only) 68.4-69.8 ms,
 // 1 -> 65.2-65.5 (28 % of the entries overflow the rings to the list), 2 -> 65.1-65.3 (none overflow), 4 -> 66.4-66.6.
-constexpr uint32_t kPbFixBatch = 2;
+#ifndef NPS_PT_FIX_BATCH
+#define NPS_PT_FIX_BATCH 2
+#endif
+constexpr uint32_t kPbFixBatch = NPS_PT_FIX_BATCH;
+template <uint32_t kFixers>
 __device__ __forceinline__ void project_fixer(const ProjTcParams& p, FixQueue* fq, uint32_t f, int lane) {
-    constexpr int kRings = 4 / kPbFixers;
+    constexpr int kRings = 4 / kFixers;
     uint32_t tail[kRings] = {};
     uint32_t live = (1u << kRings) - 1u;
     while (live) {
@@ -238,7 +253,7 @@ __device__ __forceinline__ void project_fixer(const ProjTcParams& p, FixQueue* f
 #pragma unroll
         for (int h = 0; h < kRings; ++h) {
             if (!(live >> h & 1u)) continue;
-            const uint32_t q = f + kPbFixers * h;
+            const uint32_t q = f + kFixers * h;
             uint32_t done = 0, head = 0;
             if (lane == 0) {
                 done = *reinterpret_cast<volatile uint32_t*>(&fq->done[q]);
@@ -471,37 +486,69 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& h, uint
     l = pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xFFFF0000u));
 }
 
-// Rings: raw X (kPbRawSlots x 32 KB float32: dead as soon as it is split, so it has its own, deeper
-// look-ahead) and operands (S x [x0 16 KB | x1 16 KB | w0 | w1]).  Two producer threads (X and W) so that
-// neither waits on the other's ring.
-constexpr uint32_t kPbRawSlots = 2;
-constexpr int kPbThreads = (11 + kPbFixers) * 32;   // X producer, MMA issuer, 4 epilogue, 4 splitter warps, W producer, fixer warps
+// ---------------------------------------------------------------------------------- BF16 x 2, X operand in TMEM
+// Both operands split into two BF16 terms on kind::f16 (twice the MMA rate of kind::tf32, half the operand bytes
+// per flop).  X arrives as float32 by TMA into a raw ring; eight splitter warps (thread = row = TMEM lane, two
+// groups taking alternate K-blocks) convert each 64-float K-block into x0 = rn_bf16(x), x1 = rn_bf16(x - x0) and
+// write them STRAIGHT INTO TENSOR MEMORY (tcgen05.st, 32 + 32 packed columns); the MMAs take their A operand
+// from there (tcgen05.mma [d], [a], b-desc).  The split X tiles never touch shared memory: per K-block it
+// carries 32 KB raw X in + 32 KB splitter reads + 32 KB W in + 48 KB W reads by the MMAs = 144 KB (208 KB with
+// the operands in shared memory, which was what bounded that version: C3 65 -> 50 ms).
+// TMEM: one accumulator pair [C1 | C2] in columns [0, 2 NT) — the epilogue frees it after ~0.3 us of tcgen05.ld,
+// so single buffering costs ~2 % of an item — and the A ring in columns 256 + 64 s.
+// Warps: 0 X producer, 1 MMA issuer, 2-5 epilogue, 6-9 splitters (even K-blocks), 10 W producer,
+// 11-14 splitters (odd K-blocks), 15 fixer.  16 warps = 4 per sub-partition: 128 registers.
+#ifndef NPS_PT_RAW
+#define NPS_PT_RAW 2
+#endif
+#ifndef NPS_PT_GROUPS
+#define NPS_PT_GROUPS 1
+#endif
+constexpr uint32_t kTsRawSlots = NPS_PT_RAW;
+constexpr uint32_t kTsGroups = NPS_PT_GROUPS;   // splitter groups; 2 needs even ring depths (a slot stays with its group)
+constexpr uint32_t kTsACol = 256;
+constexpr int kPbThreads = (kTsGroups == 2 ? 16 : 15) * 32;
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 
 template <uint32_t NT>
-__global__ void __launch_bounds__(kPbThreads, 1)   // 4 warps per sub-partition: 128 registers
+__global__ void __launch_bounds__(kPbThreads, 1)
 project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                     const ProjTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw);
-    const uint32_t S = p.stages;                                // operand slots
-    constexpr uint32_t R = kPbRawSlots;
+    const uint32_t S = p.stages;                                // W stages in shared memory = A slots in TMEM (<= 4)
+    constexpr uint32_t R = kTsRawSlots;
     constexpr uint32_t kWTile = NT * 128u;                      // NT projections x 64 bf16
-    constexpr uint32_t kRaw = 2u * kPtAStage, kOp = kPtAStage;  // 32 KB raw, 16 KB per bf16 X tile
-    constexpr uint32_t op_bytes = 2u * kOp + 2u * kWTile;
-    const uint32_t op_base = R * kRaw;                          // operand ring behind the raw ring
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + op_base + S * op_bytes);
+    constexpr uint32_t kRaw = 2u * kPtAStage;                   // 32 KB raw
+    constexpr uint32_t w_bytes = 2u * kWTile;
+    const uint32_t w_base = R * kRaw;                           // W ring behind the raw ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + w_base + S * w_bytes);
     uint64_t* raw_full = bars;              // [R] TMA landed the float32 tile
     uint64_t* raw_empty = raw_full + R;     // [R] splitters are done with it
     uint64_t* w_full = raw_empty + R;       // [S] TMA landed w0, w1
-    uint64_t* split_done = w_full + S;      // [S] splitters wrote x0, x1
-    uint64_t* op_empty = split_done + S;    // [S] MMAs of the slot retired
-    uint64_t* acc_full = op_empty + S;      // [2]
-    uint64_t* acc_empty = acc_full + 2;     // [2]
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* norm_s = reinterpret_cast<float*>(tmem_ptr_s + 4);   // [kPtNormBufs][128]: |x_i| from the splitters
-    FixQueue* fq = reinterpret_cast<FixQueue*>(norm_s + kPtNormBufs * kPtTileRows);
+    uint64_t* split_done = w_full + S;      // [S] splitters wrote x0, x1 into TMEM slot s
+    uint64_t* op_empty = split_done + S;    // [S] MMAs of the slot retired (W stage and A slot free)
+    uint64_t* acc_full = op_empty + S;      // [1]
+    uint64_t* acc_empty = acc_full + 1;     // [1]
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    float* norm_s = reinterpret_cast<float*>(tmem_ptr_s + 4);   // [kPtNormBufs][2][128]: sum x^2 per splitter group
+    FixQueue* fq = reinterpret_cast<FixQueue*>(norm_s + kPtNormBufs * 2u * kPtTileRows);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < 16) fq->head[tid] = 0u;   // head, tail, done, pad
@@ -515,10 +562,8 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             mbar_init(&split_done[s], 4);
             mbar_init(&op_empty[s], 1);
         }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 4);
-        }
+        mbar_init(&acc_full[0], 1);
+        mbar_init(&acc_empty[0], 4);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr_s, 512);
@@ -537,7 +582,7 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x) {
                 const unsigned long long mt = item / p.num_ntiles;
                 for (uint32_t kb = 0; kb < KB; ++kb) {
-                    mbar_wait(&raw_empty[rs], rph ^ 1u);
+                    mbar_wait_relaxed(&raw_empty[rs], rph ^ 1u);
                     const uint32_t dst = base + rs * kRaw;
                     mbar_arrive_expect_tx(&raw_full[rs], kRaw);
                     tma_load_2d(dst, &tm_x, kb * kPbKBlock, (uint32_t)(mt * kPtTileRows), &raw_full[rs]);
@@ -550,16 +595,16 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             }
         }
     } else if (warp == 10) {
-        // ===== W producer: w0 and w1 tiles straight into the operand slot
+        // ===== W producer: w0 and w1 tiles of the K-block
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
             for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x) {
                 const unsigned long long mt = item / p.num_ntiles;
                 const uint32_t nt = (uint32_t)(item - mt * p.num_ntiles);
                 for (uint32_t kb = 0; kb < KB; ++kb) {
-                    mbar_wait(&op_empty[s], ph ^ 1u);
-                    const uint32_t dst = base + op_base + s * op_bytes + 2u * kOp;
-                    mbar_arrive_expect_tx(&w_full[s], 2u * kWTile);
+                    mbar_wait_relaxed(&op_empty[s], ph ^ 1u);
+                    const uint32_t dst = base + w_base + s * w_bytes;
+                    mbar_arrive_expect_tx(&w_full[s], w_bytes);
                     tma_load_2d(dst, &tm_w, kb * kPbKBlock, nt * NT, &w_full[s]);
                     tma_load_2d(dst + kWTile, &tm_w, kb * kPbKBlock, p.B + nt * NT, &w_full[s]);
                     if (++s == S) {
@@ -570,30 +615,28 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: [C1 | C2] += x0.[w0; w1] (one instruction of width 2 NT) ; C2 += x1.w0
+        // ===== MMA issuer: [C1 | C2] += x0.[w0; w1] (one instruction of width 2 NT) ; C2 += x1.w0, A from TMEM
         const uint32_t idesc = umma_idesc(1, 1, kPtTileRows, NT);        // BF16 x BF16 -> F32
         const uint32_t idesc2 = umma_idesc(1, 1, kPtTileRows, 2u * NT);
         uint32_t s = 0, ph = 0, t_idx = 0;
+        const uint32_t c1 = tmem_base, c2 = c1 + NT;
         for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx) {
-            const uint32_t buf = t_idx & 1u;
-            mbar_wait(&acc_empty[buf], ((t_idx >> 1) & 1u) ^ 1u);
+            mbar_wait(&acc_empty[0], (t_idx & 1u) ^ 1u);
             tc_fence_after();
-            const uint32_t c1 = tmem_base + buf * (2u * NT), c2 = c1 + NT;
             for (uint32_t kb = 0; kb < KB; ++kb) {
                 mbar_wait(&w_full[s], ph);
                 mbar_wait(&split_done[s], ph);
                 tc_fence_after();
                 if (pt_elect_one()) {
-                    const uint32_t st = base + op_base + s * op_bytes;
-                    const uint64_t x0 = umma_desc_k_sw128(st), x1 = umma_desc_k_sw128(st + kOp);
-                    const uint64_t w0 = umma_desc_k_sw128(st + 2u * kOp);   // w1 follows at + kWTile
+                    const uint32_t a0 = tmem_base + kTsACol + s * 64u, a1 = a0 + 32u;
+                    const uint64_t w0 = umma_desc_k_sw128(base + w_base + s * w_bytes);   // w1 follows at + kWTile
 #pragma unroll
-                    for (uint32_t j = 0; j < 4; ++j) {   // K = 16 bf16 (32 bytes) per instruction
-                        umma_f16(c1, x0 + 2u * j, w0 + 2u * j, idesc2, (kb | j) != 0u);
-                        umma_f16(c2, x1 + 2u * j, w0 + 2u * j, idesc, true);
+                    for (uint32_t j = 0; j < 4; ++j) {   // K = 16 bf16 per instruction: 8 TMEM columns, 32 bytes of W
+                        umma_f16_ts(c1, a0 + 8u * j, w0 + 2u * j, idesc2, (kb | j) != 0u);
+                        umma_f16_ts(c2, a1 + 8u * j, w0 + 2u * j, idesc, true);
                     }
                     umma_commit(&op_empty[s]);
-                    if (kb + 1 == KB) umma_commit(&acc_full[buf]);
+                    if (kb + 1 == KB) umma_commit(&acc_full[0]);
                 }
                 __syncwarp();
                 if (++s == S) {
@@ -602,57 +645,66 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 }
             }
         }
-    } else if (warp >= 11) {
-        project_fixer(p, fq, (uint32_t)warp - 11u, lane);
+    } else if (warp >= 11 && (kTsGroups == 1 || warp == 15)) {
+        if (kTsGroups == 1) project_fixer<4>(p, fq, (uint32_t)warp - 11u, lane);
+        else project_fixer<1>(p, fq, 0u, lane);
     } else if (warp >= 6) {
-        // ===== splitters: thread = row.  Output chunk j (8 bf16 = floats 8j .. 8j+7 of the K-block) comes from
-        // 16-byte chunks 2(j&3), 2(j&3)+1 of raw box j>>2; every access is the row's 128-byte line with the
-        // chunk index XORed by (row & 7): conflict-free for the eight rows of a quarter warp.
-        const uint32_t r = (uint32_t)tid - 192u, r7 = r & 7u;
+        // ===== splitters: thread = row = TMEM lane (a warp reaches the 32 lanes of its own quarter, warp % 4); group
+        // 0 (warps 6-9) takes the even K-blocks of every item, group 1 (warps 11-14) the odd ones: one warp needs
+        // ~1000 cycles for a K-block, more than the MMAs of it.  Shared-memory reads: the row's 128-byte line with
+        // the chunk index XORed by (row & 7), conflict-free for the eight rows of a quarter warp.
+        const uint32_t group = warp >= 11 ? 1u : 0u;
+        const uint32_t quarter = (uint32_t)warp & 3u;
+        const uint32_t r = quarter * 32u + (uint32_t)lane, r7 = r & 7u;
         const uint32_t rowoff = (r >> 3) * 1024u + r7 * 128u;
-        uint32_t s = 0, ph = 0, rs = 0, rph = 0, t_idx = 0;
-        for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx) {
-            float sumsq = 0.f;      // this row sees all of its D floats pass by: |x_i| for free (no norm kernel)
-            for (uint32_t kb = 0; kb < KB; ++kb) {
+        const uint32_t t_lane = tmem_base + ((quarter * 32u) << 16) + kTsACol;
+        uint32_t t_idx = 0;
+        unsigned long long n0 = 0;      // K-blocks of this CTA before the current item
+        for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx, n0 += KB) {
+            float sumsq = 0.f;      // the two threads of a row see all of its D floats pass by: |x_i| for free
+            for (uint32_t kb = kTsGroups == 2 ? (uint32_t)((n0 ^ group) & 1u) : 0u; kb < KB; kb += kTsGroups) {
+                const unsigned long long n = n0 + kb;      // two groups: group = n & 1
+                const uint32_t rs = (uint32_t)(n % R), rph = (uint32_t)(n / R) & 1u;
+                const uint32_t s = (uint32_t)(n % S), ph = (uint32_t)(n / S) & 1u;
                 mbar_wait(&raw_full[rs], rph);
                 mbar_wait(&op_empty[s], ph ^ 1u);          // the slot's previous MMAs retired
+                tc_fence_after();
                 const uint8_t* rawp = smem + rs * kRaw;
-                uint8_t* st = smem + op_base + s * op_bytes;
+                const uint32_t t_slot = t_lane + s * 64u;
 #pragma unroll
-                for (uint32_t j = 0; j < 8; ++j) {
-                    const uint8_t* box = rawp + (j >> 2) * kPtAStage + rowoff;
-                    const uint32_t c0 = 2u * (j & 3u);
-                    const float4 a = *reinterpret_cast<const float4*>(box + ((c0 ^ r7) << 4));
-                    const float4 b = *reinterpret_cast<const float4*>(box + (((c0 + 1u) ^ r7) << 4));
-                    uint4 h, l;
-                    split_bf16x2(a.x, a.y, h.x, l.x);
-                    split_bf16x2(a.z, a.w, h.y, l.y);
-                    split_bf16x2(b.x, b.y, h.z, l.z);
-                    split_bf16x2(b.z, b.w, h.w, l.w);
-                    sumsq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, sumsq))));
-                    sumsq = fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(b.z, b.z, fmaf(b.w, b.w, sumsq))));
-                    *reinterpret_cast<uint4*>(st + rowoff + ((j ^ r7) << 4)) = h;
-                    *reinterpret_cast<uint4*>(st + kOp + rowoff + ((j ^ r7) << 4)) = l;
+                for (uint32_t jj = 0; jj < 4; ++jj) {      // 16 floats -> 8 packed columns of x0 and of x1
+                    uint32_t h[8], l[8];
+#pragma unroll
+                    for (uint32_t u = 0; u < 2; ++u) {
+                        const uint32_t j = 2u * jj + u;
+                        const uint8_t* box = rawp + (j >> 2) * kPtAStage + rowoff;
+                        const uint32_t c0 = 2u * (j & 3u);
+                        const float4 a = *reinterpret_cast<const float4*>(box + ((c0 ^ r7) << 4));
+                        const float4 b = *reinterpret_cast<const float4*>(box + (((c0 + 1u) ^ r7) << 4));
+                        split_bf16x2(a.x, a.y, h[4 * u + 0], l[4 * u + 0]);
+                        split_bf16x2(a.z, a.w, h[4 * u + 1], l[4 * u + 1]);
+                        split_bf16x2(b.x, b.y, h[4 * u + 2], l[4 * u + 2]);
+                        split_bf16x2(b.z, b.w, h[4 * u + 3], l[4 * u + 3]);
+                        sumsq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, sumsq))));
+                        sumsq = fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(b.z, b.z, fmaf(b.w, b.w, sumsq))));
+                    }
+                    tmem_st8(t_slot + 8u * jj, h);
+                    tmem_st8(t_slot + 32u + 8u * jj, l);
                 }
-                if (kb + 1 == KB) norm_s[(t_idx % kPtNormBufs) * kPtTileRows + r] = sqrtf(sumsq) * 1.001f;
-                fence_proxy_async_smem();   // generic-proxy stores -> visible to tcgen05.mma (async proxy)
+                // the group's running sum of squares: final before its last split_done of the item
+                norm_s[((t_idx % kPtNormBufs) * 2u + group) * kPtTileRows + r] = sumsq;
+                tmem_st_wait();
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&raw_empty[rs]);
                     mbar_arrive(&split_done[s]);
                 }
-                if (++rs == R) {
-                    rs = 0;
-                    rph ^= 1u;
-                }
-                if (++s == S) {
-                    s = 0;
-                    ph ^= 1u;
-                }
             }
         }
     } else {
-        project_epilogue<NT>(p, tmem_base, acc_full, acc_empty, warp, lane, total, norm_s, fq);
+        project_epilogue<NT, 1, true>(p, tmem_base, acc_full, acc_empty, warp, lane, total, norm_s, fq,
+                                      kTsGroups == 2 ? (KB >= 2u ? 2u : 3u) : 1u);
     }
     tc_fence_before();
     __syncthreads();
@@ -817,9 +869,9 @@ cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, 
     p.fix_cap = fix_cap;
     // eps: (8 + D/4) * 2^-22 for the TF32 split, (52 + D/4) * 2^-22 for the BF16 split (see the kernels)
     p.tol_scale = ((use_bf16 ? 52.0f : 8.0f) + 0.25f * (float)D) / 4194304.0f * w_norm_max;
-    // TF32: stages of [xh | xl | wh | wl]; BF16: a raw-X ring of kPbRawSlots x 32 KB + operand slots [x0 | x1 | w0 | w1]
-    const uint32_t stage_bytes = 2u * kPtAStage + 2u * n_tile * 128u;
-    const uint32_t fixed = use_bf16 ? kPbRawSlots * 2u * kPtAStage + kPtNormBufs * kPtTileRows * 4u + (uint32_t)sizeof(FixQueue) : 0u;
+    // TF32: stages of [xh | xl | wh | wl]; BF16: a raw-X ring of kTsRawSlots x 32 KB + W stages [w0 | w1] (X operand in TMEM)
+    const uint32_t stage_bytes = (use_bf16 ? 0u : 2u * kPtAStage) + 2u * n_tile * 128u;
+    const uint32_t fixed = use_bf16 ? kTsRawSlots * 2u * kPtAStage + kPtNormBufs * 2u * kPtTileRows * 4u + (uint32_t)sizeof(FixQueue) : 0u;
     uint32_t stages = (uint32_t)((smem_optin - 2048 - (int)fixed) / (int)stage_bytes);
     if (stages > 4) stages = 4;
     if (stages < 2) return cudaErrorInvalidValue;
