@@ -88,10 +88,7 @@ __device__ __forceinline__ double fix_dot(const float* __restrict__ x, const dou
 // Unsure entries on their way from the epilogue warps to the fixer warps of the same CTA: one
 // single-producer single-consumer ring per epilogue warp (quarter).  The producer never blocks: what does not
 // fit goes to the global fix-up list instead.
-#ifndef NPS_PT_FIXQ
-#define NPS_PT_FIXQ 128
-#endif
-constexpr uint32_t kPtFixQ = NPS_PT_FIXQ;
+constexpr uint32_t kPtFixQ = 128;
 struct FixQueue {
     uint32_t head[4], tail[4], done[4], pad[4];
     unsigned long long ent[4][kPtFixQ];   // row << 16 | projection
@@ -125,15 +122,13 @@ __device__ __forceinline__ uint32_t tf32_low_part(uint32_t x) {
 // Epilogue shared by both operand encodings: signs of C1 + C2 -> uint64 words; uncertain entries go to
 // the CTA's fixer warps (fq, BF16 kernel) or to the global fix-up list (one atomic per warp and item).  Accumulator buffer b holds C1 at columns [2 NT b, +NT)
 // and C2 right behind it.
-// norm_s: null -> |x_i| comes from p.norms (row_norm_kernel); else the splitter groups left their sums of
-// squares in shared memory, kPtNormBufs buffers of [norm_parts <= 2][128] floats indexed by the item count
-// (BF16 kernel).
+// norm_s: null -> |x_i| comes from p.norms (row_norm_kernel); else the splitter warps left it in shared
+// memory, kPtNormBufs buffers of 128 floats indexed by the item count (BF16 kernel).
 constexpr uint32_t kPtNormBufs = 8;   // splitters run at most 2 + stages items ahead of the epilogue
 template <uint32_t NT, uint32_t NBUF = 2, bool kRelaxed = false>
 __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t tmem_base, uint64_t* acc_full,
                                                  uint64_t* acc_empty, int warp, int lane, unsigned long long total,
-                                                 const float* norm_s = nullptr, FixQueue* fq = nullptr,
-                                                 uint32_t norm_parts = 1) {
+                                                 const float* norm_s = nullptr, FixQueue* fq = nullptr) {
         const uint32_t quarter = warp & 3u;
         const uint32_t r_in_tile = quarter * 32u + lane;
         const uint32_t words_per_row = p.B / 64u;
@@ -149,13 +144,8 @@ __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t
             if (kRelaxed) mbar_wait_relaxed(&acc_full[buf], (t_idx / NBUF) & 1u);   // sleeps in hardware, no polling
             else mbar_wait(&acc_full[buf], (t_idx / NBUF) & 1u);
             tc_fence_after();
-            if (valid && norm_s != nullptr) {    // written before the splitters' last split_done of the item
-                // norm_parts: 1 = one splitter group; 2 = two, both saw part of the row; 3 = two groups and one K-block
-                // per item: the group of this item's only K-block is t_idx & 1
-                const volatile float* ns = norm_s + (t_idx % kPtNormBufs) * 2u * kPtTileRows + r_in_tile;
-                norm = sqrtf(norm_parts == 3u ? ns[(t_idx & 1u) * kPtTileRows]
-                                              : ns[0] + (norm_parts == 2u ? ns[kPtTileRows] : 0.f)) * 1.001f;
-            }
+            if (valid && norm_s != nullptr)      // written before the splitters' last split_done of the item
+                norm = reinterpret_cast<const volatile float*>(norm_s)[(t_idx % kPtNormBufs) * kPtTileRows + r_in_tile];
             const bool tame = norm >= 1e-18f && norm <= 1e18f;     // false for 0, tiny, huge, inf, NaN
             const float tol = p.tol_scale * norm;
             const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * (2u * NT);
@@ -239,10 +229,7 @@ __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t
 // Fixer warp f of kFixers: drains rings f, f + kFixers, ... until their epilogue warps are done.
 // Entries a fixer warp recomputes together.  C3 on one B200: no fixer warps (list + project_fix_kernel only) 68.4-69.8 ms,
 // 1 -> 65.2-65.5 (28 % of the entries overflow the rings to the list), 2 -> 65.1-65.3 (none overflow), 4 -> 66.4-66.6.
-#ifndef NPS_PT_FIX_BATCH
-#define NPS_PT_FIX_BATCH 2
-#endif
-constexpr uint32_t kPbFixBatch = NPS_PT_FIX_BATCH;
+constexpr uint32_t kPbFixBatch = 2;
 template <uint32_t kFixers>
 __device__ __forceinline__ void project_fixer(const ProjTcParams& p, FixQueue* fq, uint32_t f, int lane) {
     constexpr int kRings = 4 / kFixers;
@@ -488,26 +475,23 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& h, uint
 
 // ---------------------------------------------------------------------------------- BF16 x 2, X operand in TMEM
 // Both operands split into two BF16 terms on kind::f16 (twice the MMA rate of kind::tf32, half the operand bytes
-// per flop).  X arrives as float32 by TMA into a raw ring; eight splitter warps (thread = row = TMEM lane, two
-// groups taking alternate K-blocks) convert each 64-float K-block into x0 = rn_bf16(x), x1 = rn_bf16(x - x0) and
+// per flop).  X arrives as float32 by TMA into a raw ring; four splitter warps (thread = row = TMEM lane)
+// convert each 64-float K-block into x0 = rn_bf16(x), x1 = rn_bf16(x - x0) and
 // write them STRAIGHT INTO TENSOR MEMORY (tcgen05.st, 32 + 32 packed columns); the MMAs take their A operand
 // from there (tcgen05.mma [d], [a], b-desc).  The split X tiles never touch shared memory: per K-block it
 // carries 32 KB raw X in + 32 KB splitter reads + 32 KB W in + 48 KB W reads by the MMAs = 144 KB (208 KB with
 // the operands in shared memory, which was what bounded that version: C3 65 -> 50 ms).
 // TMEM: one accumulator pair [C1 | C2] in columns [0, 2 NT) — the epilogue frees it after ~0.3 us of tcgen05.ld,
 // so single buffering costs ~2 % of an item — and the A ring in columns 256 + 64 s.
-// Warps: 0 X producer, 1 MMA issuer, 2-5 epilogue, 6-9 splitters (even K-blocks), 10 W producer,
-// 11-14 splitters (odd K-blocks), 15 fixer.  16 warps = 4 per sub-partition: 128 registers.
-#ifndef NPS_PT_RAW
-#define NPS_PT_RAW 2
-#endif
-#ifndef NPS_PT_GROUPS
-#define NPS_PT_GROUPS 1
-#endif
-constexpr uint32_t kTsRawSlots = NPS_PT_RAW;
-constexpr uint32_t kTsGroups = NPS_PT_GROUPS;   // splitter groups; 2 needs even ring depths (a slot stays with its group)
+// Warps: 0 X producer, 1 MMA issuer, 2-5 epilogue, 6-9 splitters, 10 W producer, 11-14 fixers (15 warps: four on
+// a sub-partition, hence 128 registers).
+// Tried and measured on C3 (10M x 768 -> 1024 bit; this layout: 50-52 ms): a second splitter group on alternate
+// K-blocks with one fixer warp left (main kernel -10 %, but 11 M instead of 3 M pairs fall through to
+// project_fix_kernel: 53.7 ms); 3 raw slots + 3 W stages (61.7 ms: the W ring needs its four stages); CTA pairs
+// (cta_group::2, each CTA staging half of every W tile, 2-5 raw slots: 54-69 ms, the deeper the raw ring the slower).
+constexpr uint32_t kTsRawSlots = 2;
 constexpr uint32_t kTsACol = 256;
-constexpr int kPbThreads = (kTsGroups == 2 ? 16 : 15) * 32;
+constexpr int kPbThreads = 15 * 32;
 
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -547,8 +531,8 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     uint64_t* acc_full = op_empty + S;      // [1]
     uint64_t* acc_empty = acc_full + 1;     // [1]
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc_empty + 1);
-    float* norm_s = reinterpret_cast<float*>(tmem_ptr_s + 4);   // [kPtNormBufs][2][128]: sum x^2 per splitter group
-    FixQueue* fq = reinterpret_cast<FixQueue*>(norm_s + kPtNormBufs * 2u * kPtTileRows);
+    float* norm_s = reinterpret_cast<float*>(tmem_ptr_s + 4);   // [kPtNormBufs][128]: |x_i| from the splitters
+    FixQueue* fq = reinterpret_cast<FixQueue*>(norm_s + kPtNormBufs * kPtTileRows);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < 16) fq->head[tid] = 0u;   // head, tail, done, pad
@@ -645,27 +629,20 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 }
             }
         }
-    } else if (warp >= 11 && (kTsGroups == 1 || warp == 15)) {
-        if (kTsGroups == 1) project_fixer<4>(p, fq, (uint32_t)warp - 11u, lane);
-        else project_fixer<1>(p, fq, 0u, lane);
+    } else if (warp >= 11) {
+        project_fixer<4>(p, fq, (uint32_t)warp - 11u, lane);
     } else if (warp >= 6) {
-        // ===== splitters: thread = row = TMEM lane (a warp reaches the 32 lanes of its own quarter, warp % 4); group
-        // 0 (warps 6-9) takes the even K-blocks of every item, group 1 (warps 11-14) the odd ones: one warp needs
-        // ~1000 cycles for a K-block, more than the MMAs of it.  Shared-memory reads: the row's 128-byte line with
-        // the chunk index XORed by (row & 7), conflict-free for the eight rows of a quarter warp.
-        const uint32_t group = warp >= 11 ? 1u : 0u;
+        // ===== splitters: thread = row = TMEM lane (a warp reaches the 32 lanes of its own quarter, warp % 4).
+        // Shared-memory reads: the row's 128-byte line with the chunk index XORed by (row & 7), conflict-free for
+        // the eight rows of a quarter warp.
         const uint32_t quarter = (uint32_t)warp & 3u;
         const uint32_t r = quarter * 32u + (uint32_t)lane, r7 = r & 7u;
         const uint32_t rowoff = (r >> 3) * 1024u + r7 * 128u;
         const uint32_t t_lane = tmem_base + ((quarter * 32u) << 16) + kTsACol;
-        uint32_t t_idx = 0;
-        unsigned long long n0 = 0;      // K-blocks of this CTA before the current item
-        for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx, n0 += KB) {
-            float sumsq = 0.f;      // the two threads of a row see all of its D floats pass by: |x_i| for free
-            for (uint32_t kb = kTsGroups == 2 ? (uint32_t)((n0 ^ group) & 1u) : 0u; kb < KB; kb += kTsGroups) {
-                const unsigned long long n = n0 + kb;      // two groups: group = n & 1
-                const uint32_t rs = (uint32_t)(n % R), rph = (uint32_t)(n / R) & 1u;
-                const uint32_t s = (uint32_t)(n % S), ph = (uint32_t)(n / S) & 1u;
+        uint32_t s = 0, ph = 0, rs = 0, rph = 0, t_idx = 0;
+        for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx) {
+            float sumsq = 0.f;      // this row sees all of its D floats pass by: |x_i| for free (no norm kernel)
+            for (uint32_t kb = 0; kb < KB; ++kb) {
                 mbar_wait(&raw_full[rs], rph);
                 mbar_wait(&op_empty[s], ph ^ 1u);          // the slot's previous MMAs retired
                 tc_fence_after();
@@ -691,8 +668,7 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                     tmem_st8(t_slot + 8u * jj, h);
                     tmem_st8(t_slot + 32u + 8u * jj, l);
                 }
-                // the group's running sum of squares: final before its last split_done of the item
-                norm_s[((t_idx % kPtNormBufs) * 2u + group) * kPtTileRows + r] = sumsq;
+                if (kb + 1 == KB) norm_s[(t_idx % kPtNormBufs) * kPtTileRows + r] = sqrtf(sumsq) * 1.001f;
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -700,11 +676,18 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                     mbar_arrive(&raw_empty[rs]);
                     mbar_arrive(&split_done[s]);
                 }
+                if (++rs == R) {
+                    rs = 0;
+                    rph ^= 1u;
+                }
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1u;
+                }
             }
         }
     } else {
-        project_epilogue<NT, 1, true>(p, tmem_base, acc_full, acc_empty, warp, lane, total, norm_s, fq,
-                                      kTsGroups == 2 ? (KB >= 2u ? 2u : 3u) : 1u);
+        project_epilogue<NT, 1, true>(p, tmem_base, acc_full, acc_empty, warp, lane, total, norm_s, fq);
     }
     tc_fence_before();
     __syncthreads();
@@ -871,7 +854,7 @@ cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, 
     p.tol_scale = ((use_bf16 ? 52.0f : 8.0f) + 0.25f * (float)D) / 4194304.0f * w_norm_max;
     // TF32: stages of [xh | xl | wh | wl]; BF16: a raw-X ring of kTsRawSlots x 32 KB + W stages [w0 | w1] (X operand in TMEM)
     const uint32_t stage_bytes = (use_bf16 ? 0u : 2u * kPtAStage) + 2u * n_tile * 128u;
-    const uint32_t fixed = use_bf16 ? kTsRawSlots * 2u * kPtAStage + kPtNormBufs * 2u * kPtTileRows * 4u + (uint32_t)sizeof(FixQueue) : 0u;
+    const uint32_t fixed = use_bf16 ? kTsRawSlots * 2u * kPtAStage + kPtNormBufs * kPtTileRows * 4u + (uint32_t)sizeof(FixQueue) : 0u;
     uint32_t stages = (uint32_t)((smem_optin - 2048 - (int)fixed) / (int)stage_bytes);
     if (stages > 4) stages = 4;
     if (stages < 2) return cudaErrorInvalidValue;
