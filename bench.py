@@ -604,7 +604,8 @@ def run_c3(args, torch, dist, dev, rank, world, timer, pk):
                                  "(xh*wh + xh*wl + xl*wh); peak = measured bf16 burst x n_gpus",
                          "input_gbs_per_gpu": n_local * dims * 4 / t / 1e9, "hbm_peak_gbs": pk["hbm"]},
             "gpu_launches_per_step": int(launches // args.c3_steps),
-            "hash": {"recomputed_in_float64": st.get("recomputed"), "pairs": st.get("pairs"), "overflowed": st.get("overflowed"),
+            "hash": {"recomputed_in_float64": st.get("recomputed"), "by_fixer_warps_in_kernel": st.get("in_kernel"),
+                     "by_fix_up_list": st.get("listed"), "pairs": st.get("pairs"), "overflowed": st.get("overflowed"),
                      "rows_checked_vs_float64_oracle": int(n_sub), "flipped_bits_before_fixup": flipped_raw,
                      "flipped_bit_rate_before_fixup": flipped_raw / (n_sub * bits), "flipped_bits_final": flipped},
         }

@@ -233,14 +233,15 @@ int nps_rerank_top_n(const uint64_t *d_hashes, uint64_t num_hashes, uint32_t wor
  * the kernel, w = wh + wl by nps_project_split_projections) and three products are accumulated, so
  * an accumulator is exact to (8 + dims / 4) * 2^-22 * |x_i| * projection_norm_max; the (row,
  * projection) pairs below that (0.03 % at dims = 300) and all rows with a zero / tiny / huge /
- * non-finite norm are recomputed in float64 by a fix-up kernel, so the signatures equal those of
- * nps_project_sign_pack_f64.  Needs dims % 4 == 0 and 16-byte aligned inputs.
+ * non-finite norm are recomputed in float64 — by fixer warps inside the hashing kernel (BF16 encoding) or,
+ * listed, by a fix-up kernel — so the signatures equal those of nps_project_sign_pack_f64.  Needs dims % 4 == 0 and 16-byte aligned inputs.
  * d_projections_split: nps_project_split_bytes() bytes filled by nps_project_split_projections (do it
  * once per projection matrix); d_projections_f64: the float64 matrix (fix-up);
  * projection_norm_max = max_j |projections[j]| (1.0 for lsh.create_projections).
  * If the fix-up list overflows (degenerate input) the call is redone in float64 by a gated launch
  * on the device — no host round trip.  nps_project_sign_pack_stats (diagnostic; synchronises the
- * stream) returns how many pairs went to the fix-up list and its capacity. */
+ * stream) returns how many pairs went to the fix-up list and its capacity (listed > capacity: the call was redone
+ * in float64); nps_project_sign_pack_stats_in_kernel how many more the fixer warps recomputed inside the kernel. */
 /* size in bytes of the split buffer for nps_project_split_projections / nps_project_sign_pack (both
  * operand encodings: float32 [2, B, dims] TF32 parts, then bfloat16 [2, B, dims rounded up to 8]) */
 size_t nps_project_split_bytes(uint32_t num_projections, uint32_t dims);
@@ -259,6 +260,8 @@ int nps_project_sign_pack(const float *d_vectors, uint64_t num_vectors, uint32_t
                           void *d_workspace, size_t workspace_bytes, void *stream);
 int nps_project_sign_pack_stats(const void *d_workspace, uint64_t num_vectors, uint32_t num_projections,
                                 void *stream, uint32_t *recomputed, uint32_t *capacity);
+int nps_project_sign_pack_stats_in_kernel(const void *d_workspace, uint64_t num_vectors, void *stream,
+                                          uint32_t *in_kernel);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

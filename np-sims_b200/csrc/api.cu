@@ -711,6 +711,16 @@ int nps_project_sign_pack_stats(const void* d_workspace, uint64_t num_vectors, u
     return NPS_OK;
 }
 
+int nps_project_sign_pack_stats_in_kernel(const void* d_workspace, uint64_t num_vectors, void* stream,
+                                          uint32_t* in_kernel) {
+    if (!d_workspace || !in_kernel) return fail(NPS_EINVAL, "null pointer");
+    const size_t off = ((size_t)num_vectors * 4 + 255) / 256 * 256 + 4;
+    NPS_CUDA(cudaMemcpyAsync(in_kernel, reinterpret_cast<const uint8_t*>(d_workspace) + off, 4, cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+    NPS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return NPS_OK;
+}
+
 // ------------------------------------------------------------------------------ host level
 struct nps_index {
     int device = 0;

@@ -56,7 +56,7 @@ struct ProjTcParams {
     uint64_t* out;              // [N, B/64]
     const float* norms;         // [N] |x_i|
     unsigned long long* fix;    // [fix_cap] row << 16 | projection
-    unsigned int* fix_count;    // [1]
+    unsigned int* fix_count;    // [2]: pairs sent to the list (saturating), pairs recomputed by the fixer warps
     unsigned long long N;
     uint32_t D, B, num_ntiles, stages, fix_cap;
     float tol_scale;            // eps * max_j |w_j|
@@ -203,7 +203,10 @@ __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t
                     __threadfence_block();     // words and entries before the new head
                     __syncwarp();
                     q_head += all;
-                    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&fq->head[quarter]) = q_head;
+                    if (lane == 0) {
+                        *reinterpret_cast<volatile uint32_t*>(&fq->head[quarter]) = q_head;
+                        atomicAdd(p.fix_count + 1, all);     // statistics only
+                    }
                     all = 0;
                 }
             }
@@ -870,7 +873,7 @@ cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, 
         return cudaErrorInvalidValue;
     }
 
-    cudaError_t e = cudaMemsetAsync(fix_count, 0, 4, stream);
+    cudaError_t e = cudaMemsetAsync(fix_count, 0, 8, stream);
     if (e != cudaSuccess) return e;
     if (!use_bf16) {   // the BF16 kernel's splitter warps compute |x_i| on the way
         row_norm_kernel<<<(unsigned)((N + 7) / 8), 256, 0, stream>>>(X, N, D, norms);

@@ -68,6 +68,7 @@ _SIGS = {
     "nps_set_hash_path": (_int, [_int]),
     "nps_project_sign_pack": (_int, [_vp, _u64, _u32, _vp, _vp, _u32, ctypes.c_float, _vp, _vp, _sz, _vp]),
     "nps_project_sign_pack_stats": (_int, [_vp, _u64, _u32, _vp, ctypes.POINTER(_u32), ctypes.POINTER(_u32)]),
+    "nps_project_sign_pack_stats_in_kernel": (_int, [_vp, _u64, _vp, ctypes.POINTER(_u32)]),
     "nps_project_sign_pack_f64": (_int, [_vp, _int, _u64, _u32, _vp, _u32, _vp, _vp, _vp]),
 }
 for _name, (_res, _args) in _SIGS.items():

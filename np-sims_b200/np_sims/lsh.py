@@ -73,24 +73,25 @@ _last_hash_ws = None
 
 def hash_stats():
     """Diagnostics (tests / bench): `last_hash_stats` with `recomputed` filled in — the number of
-    pairs whose accumulator was too close to zero to trust and that were recomputed in float64;
-    `overflowed` says the fix-up list was too small and the whole call was redone in float64 on
+    pairs whose accumulator was too close to zero to trust and that were recomputed in float64, by the
+    fixer warps inside the hashing kernel (`in_kernel`) or through the fix-up list (`listed`);
+    `overflowed` says the list was too small and the whole call was redone in float64 on
     the device.  Synchronises the stream; the hashing call itself never does."""
     st = dict(last_hash_stats)
     if st["path"] == "tc-split+fixup" and _last_hash_ws is not None:
         counter, cap = _last_hash_ws
-        fixed = int(counter.cpu().numpy().view(np.uint32)[0])
-        st.update(recomputed=fixed, overflowed=fixed > cap)
+        listed, in_kernel = (int(v) for v in counter.cpu().numpy().view(np.uint32)[:2])
+        st.update(recomputed=listed + in_kernel, listed=listed, in_kernel=in_kernel, overflowed=listed > cap)
     return st
 
 
 def _remember_hash_workspace(ws, ws_bytes, n):
     """Keep what `hash_stats` needs from the K1T workspace (layout, project_tc.cu: |x| norms, then the
-    fix-up counter, then the list): a 4-byte copy of the counter and the list capacity — not the
+    fix-up counters, then the list): an 8-byte copy of the counters and the list capacity — not the
     workspace itself, which is 10 GB for the C3 table."""
     global _last_hash_ws
     off = (4 * n + 255) // 256 * 256
-    _last_hash_ws = (ws[off:off + 4].clone(), (ws_bytes - off - 256) // 8)
+    _last_hash_ws = (ws[off:off + 8].clone(), (ws_bytes - off - 256) // 8)
 
 
 def _projections_split(projections, P64):

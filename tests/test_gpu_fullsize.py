@@ -143,3 +143,35 @@ def test_narrow_signatures_large_batch_vs_oracle(nps, w, pair):
     finally:
         _lib.raw("nps_set_mma_pair")(1)
         _lib.set_scan_path(prev)
+
+
+@pytest.mark.gpu
+def test_hash_fixer_rings_under_pressure_vs_float64_oracle(nps):
+    """K1T at a size where every CTA works through many tiles (150k x 768 -> 1024 bit): ordinary rows, whose
+    unsure pairs travel through the fixer warps' shared-memory rings, interleaved with runs of degenerate rows
+    (zero / tiny / huge / inf / NaN: all 1024 pairs of such a row are unsure, which overflows a ring into the global
+    fix-up list while other entries are in flight).  Both routes and their mixture must give the float64 oracle's
+    signatures bit for bit."""
+    import np_sims.lsh as lsh
+    n, dims, bits = 150_000, 768, 1024
+    rng = np.random.default_rng(2024)
+    X = rng.standard_normal((n, dims), dtype=np.float32)
+    X[::3] *= rng.uniform(1e-3, 1e3, size=(len(X[::3]), 1)).astype(np.float32)
+    bad = rng.choice(n, size=1200, replace=False)
+    bad[:200] = np.arange(5000, 5200)                 # a contiguous run: whole tiles of degenerate rows
+    X[bad[0:300]] = 0.0
+    X[bad[300:600]] *= np.float32(1e-25)
+    X[bad[600:900]] *= np.float32(1e25)
+    X[bad[900:1050], 5] = np.inf
+    X[bad[1050:1200], 7] = np.nan
+    np.random.seed(3)
+    W = lsh.create_projections(bits, dims)
+    with np.errstate(all="ignore"):
+        want = oracle.index_np(X, np.asarray(W))
+    got = np.asarray(lsh.index(X, W))
+    st = lsh.hash_stats()
+    assert st["path"] == "tc-split+fixup" and not st["overflowed"]
+    assert st["in_kernel"] > 0 and st["listed"] >= 200 * bits, st          # both routes were taken
+    assert st["recomputed"] >= len(set(bad.tolist())) * bits, st
+    diff = got ^ want
+    assert not diff.any(), f"{np.count_nonzero(diff.any(axis=1))} rows differ; first {np.flatnonzero(diff.any(axis=1))[:8]}"
