@@ -53,7 +53,9 @@ struct MmaScanParams {
     const uint64_t* hashes;    // [N, W] bit-packed
     const uint64_t* queries;   // [Q, W] bit-packed
     const float* thrT;         // [Qpad]  pass iff dot >= thrT[q]   (-inf: everything, +inf: nothing)
-    const uint64_t* thrK;      // [Qpad]  exact test: key < thrK[q]
+    const uint64_t* thrK;      // [Qpad]  the current k-th key (written by the select).  NOT read by the scan: rows tied with
+                               //         it at the k-th distance are appended again and dropped by the select — applying
+                               //         key < thrK[q] at flush time was measured (+5 % on C2) and not kept
     uint64_t* cand;            // [Q, cap] candidate keys
     uint32_t* cnt;             // [Q] candidates appended this phase
     uint32_t* overflow;        // [1] bumped if a warp's staging buffer overflowed (results then not final)
