@@ -908,7 +908,8 @@ def run_b200(args, wl):
         s_oracle = oracle.index_np(qvecs_host, np.asarray(W))
         hash_report = {"path": st["path"], "bits": nbits,
                        "encoding": "bf16 x 2 (kind::f16), three products, separate correction accumulator",
-                       "tolerance": f"(52 + dims/4) * 2^-22 * |x| * max|w| = {(52 + wl['dims'] / 4) * 2.0 ** -22:.3e} |x|",
+                       "tolerance": f"(52 + 0.006 dims) * 2^-22 |x| max|w| + 2.68 * 2^-22 * sum_i |x[0:16i)| max_j |w_j[0:16i)| "
+                                    f"<= (52 + 0.17 dims) * 2^-22 |x| max|w| = {(52 + 0.17 * wl['dims']) * 2.0 ** -22:.3e} |x|",
                        "recomputed_in_float64": st.get("recomputed"), "recomputed_frac": (st.get("recomputed") or 0) / nbits,
                        "flipped_bits_before_fixup": bits_differing(s_raw, s_exact),
                        "flipped_bits_final": bits_differing(s_final, s_exact),

@@ -243,10 +243,12 @@ int nps_rerank_top_n(const uint64_t *d_hashes, uint64_t num_hashes, uint32_t wor
  * stream) returns how many pairs went to the fix-up list and its capacity (listed > capacity: the call was redone
  * in float64); nps_project_sign_pack_stats_in_kernel how many more the fixer warps recomputed inside the kernel. */
 /* size in bytes of the split buffer for nps_project_split_projections / nps_project_sign_pack (both
- * operand encodings: float32 [2, B, dims] TF32 parts, then bfloat16 [2, B, dims rounded up to 8]) */
+ * operand encodings: float32 [2, B, dims] TF32 parts, then bfloat16 [2, B, dims rounded up to 8], then the
+ * projections' prefix norms max_j |w_j[0 : 16 i)|, one float32 per 16 dims, for the BF16 kernel's tolerance) */
 size_t nps_project_split_bytes(uint32_t num_projections, uint32_t dims);
 /* which operand encoding nps_project_sign_pack uses: BF16 x 2 on kind::f16 (AUTO, the default; tolerance
- * (52 + dims/4) * 2^-22) or TF32 x 2 on kind::tf32 (tolerance (8 + dims/4) * 2^-22) */
+ * (52 + 0.006 dims) * 2^-22 |x| max|w| + 2.68 * 2^-22 * sum_i |x[0 : 16 i)| max_j |w_j[0 : 16 i)|, at most
+ * (52 + 0.17 dims) * 2^-22 |x| max|w|) or TF32 x 2 on kind::tf32 (tolerance (8 + dims/4) * 2^-22 |x| max|w|) */
 #define NPS_HASH_AUTO 0
 #define NPS_HASH_TF32 1
 #define NPS_HASH_BF16 2

@@ -59,7 +59,9 @@ struct ProjTcParams {
     unsigned int* fix_count;    // [2]: pairs sent to the list (saturating), pairs recomputed by the fixer warps
     unsigned long long N;
     uint32_t D, B, num_ntiles, stages, fix_cap;
-    float tol_scale;            // eps * max_j |w_j|
+    float tol_scale;            // eps * max_j |w_j|: the part of the tolerance that scales with |x_i|
+    float acc_scale;            // BF16 kernel: factor of the accumulation term, sum_i |x_i[0 : 16 i)| qtab[i]
+    const float* qtab;          // BF16 kernel: [4 * K-blocks] max_j |w_j[0 : 16 (i + 1))|
     unsigned long long num_mtiles;
     const float* X;             // [N, D] the rows again, for the float64 recomputation in the epilogue
     const double* W64;          // [B, D]
@@ -128,7 +130,8 @@ constexpr uint32_t kPtNormBufs = 8;   // splitters run at most 2 + stages items 
 template <uint32_t NT, uint32_t NBUF = 2, bool kRelaxed = false>
 __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t tmem_base, uint64_t* acc_full,
                                                  uint64_t* acc_empty, int warp, int lane, unsigned long long total,
-                                                 const float* norm_s = nullptr, FixQueue* fq = nullptr) {
+                                                 const float* norm_s = nullptr, FixQueue* fq = nullptr,
+                                                 const float* acc_s = nullptr) {
         const uint32_t quarter = warp & 3u;
         const uint32_t r_in_tile = quarter * 32u + lane;
         const uint32_t words_per_row = p.B / 64u;
@@ -147,7 +150,10 @@ __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t
             if (valid && norm_s != nullptr)      // written before the splitters' last split_done of the item
                 norm = reinterpret_cast<const volatile float*>(norm_s)[(t_idx % kPtNormBufs) * kPtTileRows + r_in_tile];
             const bool tame = norm >= 1e-18f && norm <= 1e18f;     // false for 0, tiny, huge, inf, NaN
-            const float tol = p.tol_scale * norm;
+            // BF16 kernel: + the accumulation term the splitters summed up for this row (see the kernel's header)
+            float tol = p.tol_scale * norm;
+            if (acc_s != nullptr)
+                tol = fmaf(p.acc_scale, reinterpret_cast<const volatile float*>(acc_s)[(t_idx % kPtNormBufs) * kPtTileRows + r_in_tile], tol);
             const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * (2u * NT);
             uint32_t sign_m[G], unsure_m[G];
 #pragma unroll
@@ -460,7 +466,16 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 // bits, RZ write-back): per instruction (K = 16) (17/4 + 1) * 2^-23.  Budget relative to |x||w|:
 //      representation  x1.w1 + ex.w + x.ew        3 * 2^-18               =  48 * 2^-22
 //      C1 accumulation D/16 instructions x 5.25 * 2^-23                   =  0.164 * D * 2^-22
-// -> trusted when |C1 + C2| >= (52 + D/4) * 2^-22 * |x_i| max_j |w_j|.
+//      C2 accumulation (at 2^-8 of the scale), final add                  <= (0.001 D + 0.25) * 2^-22
+// The accumulation term is relative to the largest partial sum an instruction sees, and instruction i (elements
+// [16 i, 16 i + 16)) sees at most sum_{k < 16 (i+1)} |x_k w_k| <= |x[0 : 16 (i+1))| |w[0 : 16 (i+1))|: the PREFIX
+// norms (Cauchy-Schwarz on the prefix), not the full ones.  The splitter thread of a row has the running sum of
+// squares anyway; it adds up  P = sum_i |x[0 : 16 (i+1))| qtab[i],  qtab[i] = max_j |w_j[0 : 16 (i+1))| (48 floats
+// at D = 768, from split_projections), and the row's tolerance is
+//      (52 + 0.006 D) * 2^-22 * |x| max_j |w_j|  +  2.625 * 1.02 * 2^-22 * P
+// (1.02: |x0_k| <= (1 + 2^-8) |x_k|, the same for w0, float32 rounding of P).  For rows and projections without
+// structure P ~ |x||w| D/32, half of the full-norm bound: 0.096 % of the pairs are unsure at D = 768 with the
+// full norms, about 0.06 % with the prefix norms.
 // Stage layout: [raw fp32 2 x 16 KB][x0 16 KB][x1 16 KB][w0 NT x 128 B][w1 NT x 128 B]
 // =============================================================================================
 constexpr int kPbKBlock = 64;
@@ -535,7 +550,8 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     uint64_t* acc_empty = acc_full + 1;     // [1]
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc_empty + 1);
     float* norm_s = reinterpret_cast<float*>(tmem_ptr_s + 4);   // [kPtNormBufs][128]: |x_i| from the splitters
-    FixQueue* fq = reinterpret_cast<FixQueue*>(norm_s + kPtNormBufs * kPtTileRows);
+    float* acc_s = norm_s + kPtNormBufs * kPtTileRows;          // [kPtNormBufs][128]: sum_i |x_i[0 : 16 i)| qtab[i]
+    FixQueue* fq = reinterpret_cast<FixQueue*>(acc_s + kPtNormBufs * kPtTileRows);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < 16) fq->head[tid] = 0u;   // head, tail, done, pad
@@ -645,7 +661,9 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         uint32_t s = 0, ph = 0, rs = 0, rph = 0, t_idx = 0;
         for (unsigned long long item = blockIdx.x; item < total; item += gridDim.x, ++t_idx) {
             float sumsq = 0.f;      // this row sees all of its D floats pass by: |x_i| for free (no norm kernel)
+            float pacc = 0.f;       // sum over the MMA instructions (16 elements each) of |x_i[0 : 16 (i + 1))| qtab[i]
             for (uint32_t kb = 0; kb < KB; ++kb) {
+                const float4 qt = __ldg(reinterpret_cast<const float4*>(p.qtab) + kb);   // in flight during the waits
                 mbar_wait(&raw_full[rs], rph);
                 mbar_wait(&op_empty[s], ph ^ 1u);          // the slot's previous MMAs retired
                 tc_fence_after();
@@ -670,8 +688,14 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                     }
                     tmem_st8(t_slot + 8u * jj, h);
                     tmem_st8(t_slot + 32u + 8u * jj, l);
+                    float prefix;      // |x[0 : 16 (i + 1))|: MUFU.SQRT (2 ulp) is plenty against the 1.02
+                    asm("sqrt.approx.f32 %0, %1;" : "=f"(prefix) : "f"(sumsq));
+                    pacc = fmaf(prefix, jj == 0 ? qt.x : jj == 1 ? qt.y : jj == 2 ? qt.z : qt.w, pacc);
                 }
-                if (kb + 1 == KB) norm_s[(t_idx % kPtNormBufs) * kPtTileRows + r] = sqrtf(sumsq) * 1.001f;
+                if (kb + 1 == KB) {
+                    norm_s[(t_idx % kPtNormBufs) * kPtTileRows + r] = sqrtf(sumsq) * 1.001f;
+                    acc_s[(t_idx % kPtNormBufs) * kPtTileRows + r] = pacc;
+                }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -690,7 +714,7 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             }
         }
     } else {
-        project_epilogue<NT, 1, true>(p, tmem_base, acc_full, acc_empty, warp, lane, total, norm_s, fq);
+        project_epilogue<NT, 1, true>(p, tmem_base, acc_full, acc_empty, warp, lane, total, norm_s, fq, acc_s);
     }
     tc_fence_before();
     __syncthreads();
@@ -701,9 +725,14 @@ project_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
 //   [2, B, D]  float32  wh = rn_tf32(w), wl = rn_tf32(w - wh)          w - wh - wl <= 2^-22 |w|
 //   [2, B, Dp] bfloat16 w0 = rn_bf16(w), w1 = rn_bf16(w - w0), Dp = D rounded up to 8 (16-byte rows for
 //              the tensor map), zero padded                             w - w0 - w1 <= 2^-18 |w|
+//   [4 * ceil(D / 64)] float32  qtab[i] = max_j |w_j[0 : 16 (i + 1))|_2: prefix norms for the BF16 kernel's tolerance
 static size_t split_tf32_bytes(uint32_t B, uint32_t D) { return ((size_t)2 * B * D * 4 + 255) / 256 * 256; }
 static uint32_t split_dp(uint32_t D) { return (D + 7u) & ~7u; }
-size_t project_split_bytes(uint32_t B, uint32_t D) { return split_tf32_bytes(B, D) + (size_t)2 * B * split_dp(D) * 2; }
+static size_t split_bf16_bytes(uint32_t B, uint32_t D) { return ((size_t)2 * B * split_dp(D) * 2 + 255) / 256 * 256; }
+static uint32_t split_qtab_len(uint32_t D) { return (D + 63u) / 64u * 4u; }     // one entry per MMA instruction
+size_t project_split_bytes(uint32_t B, uint32_t D) {
+    return split_tf32_bytes(B, D) + split_bf16_bytes(B, D) + (size_t)split_qtab_len(D) * 4;
+}
 
 __global__ void __launch_bounds__(256) split_projections_kernel(const double* __restrict__ W, uint32_t B, uint32_t D,
                                                                 uint32_t Dp, float* __restrict__ out,
@@ -724,11 +753,44 @@ __global__ void __launch_bounds__(256) split_projections_kernel(const double* __
     out16[(size_t)B * Dp + i] = (uint16_t)b1;
 }
 
+// qtab[i] = max over the projections of |w_j[0 : 16 (i + 1))|_2 (non-negative floats order like their bit patterns):
+// one warp per projection, lane l owns the 16-element blocks l, l + 32, ...
+__global__ void __launch_bounds__(256) prefix_norm_kernel(const double* __restrict__ W, uint32_t B, uint32_t D,
+                                                          uint32_t len, float* __restrict__ qtab) {
+    const uint32_t j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (j >= B) return;
+    double before = 0.0;        // sum of squares of all blocks before this round of 32
+    for (uint32_t i0 = 0; i0 < len; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        double mine = 0.0;
+        for (uint32_t k = 16u * i; k < 16u * i + 16u && k < D; ++k) {
+            const double w = W[(size_t)j * D + k];
+            mine += w * w;
+        }
+        double incl = mine;     // inclusive prefix sum over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (i < len) atomicMax(reinterpret_cast<unsigned int*>(qtab + i), __float_as_uint((float)sqrt(before + incl) * 1.0001f));
+        before += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
 cudaError_t launch_split_projections(const double* W64, uint32_t B, uint32_t D, float* out, cudaStream_t stream) {
     const size_t n = (size_t)B * split_dp(D);
     if (n == 0) return cudaSuccess;
     uint16_t* out16 = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(out) + split_tf32_bytes(B, D));
     split_projections_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(W64, B, D, split_dp(D), out, out16);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    float* qtab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(out16) + split_bf16_bytes(B, D));
+    e = cudaMemsetAsync(qtab, 0, (size_t)split_qtab_len(D) * 4, stream);
+    if (e != cudaSuccess) return e;
+    prefix_norm_kernel<<<(B + 7) / 8, 256, 0, stream>>>(W64, B, D, split_qtab_len(D), qtab);
     count_launch();
     return cudaGetLastError();
 }
@@ -853,11 +915,13 @@ cudaError_t launch_project_tc(const float* X, unsigned long long N, uint32_t D, 
     p.num_ntiles = B / n_tile;
     p.num_mtiles = (N + kPtTileRows - 1) / kPtTileRows;
     p.fix_cap = fix_cap;
-    // eps: (8 + D/4) * 2^-22 for the TF32 split, (52 + D/4) * 2^-22 for the BF16 split (see the kernels)
-    p.tol_scale = ((use_bf16 ? 52.0f : 8.0f) + 0.25f * (float)D) / 4194304.0f * w_norm_max;
+    // eps: (8 + D/4) * 2^-22 for the TF32 split; BF16: (52 + 0.006 D) * 2^-22 + the prefix-norm accumulation term (see the kernels)
+    p.tol_scale = (use_bf16 ? 52.0f + 0.006f * (float)D : 8.0f + 0.25f * (float)D) / 4194304.0f * w_norm_max;
+    p.acc_scale = w_norm_max < 1e-20f ? 0.f : 2.625f * 1.02f / 4194304.0f;   // (tiny norm: the raw-signs measurement mode)
+    p.qtab = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(Wsplit) + split_tf32_bytes(B, D) + split_bf16_bytes(B, D));
     // TF32: stages of [xh | xl | wh | wl]; BF16: a raw-X ring of kTsRawSlots x 32 KB + W stages [w0 | w1] (X operand in TMEM)
     const uint32_t stage_bytes = (use_bf16 ? 0u : 2u * kPtAStage) + 2u * n_tile * 128u;
-    const uint32_t fixed = use_bf16 ? kTsRawSlots * 2u * kPtAStage + kPtNormBufs * kPtTileRows * 4u + (uint32_t)sizeof(FixQueue) : 0u;
+    const uint32_t fixed = use_bf16 ? kTsRawSlots * 2u * kPtAStage + 2u * kPtNormBufs * kPtTileRows * 4u + (uint32_t)sizeof(FixQueue) : 0u;
     uint32_t stages = (uint32_t)((smem_optin - 2048 - (int)fixed) / (int)stage_bytes);
     if (stages > 4) stages = 4;
     if (stages < 2) return cudaErrorInvalidValue;

@@ -96,7 +96,8 @@ def test_hash_split_buffer_size_and_path_switch_need_no_gpu():
     from np_sims import _lib
     size = _lib.raw("nps_project_split_bytes")(640, 300)
     tf32 = (2 * 640 * 300 * 4 + 255) // 256 * 256              # float32 [2, B, D]
-    assert size == tf32 + 2 * 640 * 304 * 2                    # + bfloat16 [2, B, D rounded up to 8]
+    bf16 = (2 * 640 * 304 * 2 + 255) // 256 * 256              # bfloat16 [2, B, D rounded up to 8]
+    assert size == tf32 + bf16 + 4 * 5 * 4                     # + float32 prefix norms, one per 16 dims of 5 K-blocks
     assert _lib.raw("nps_set_hash_path")(7) != 0 and "hash path" in _lib.last_error()
     for path in (_lib.HASH_TF32, _lib.HASH_BF16, _lib.HASH_AUTO):
         assert _lib.raw("nps_set_hash_path")(path) == 0
