@@ -347,8 +347,9 @@ def test_torch_tensor_inputs_stay_on_device(nps):
 def test_tensor_core_hash_equals_float64_oracle(nps, n, dims, bits):
     """K1T (tcgen05 GEMM on two-term splits of both operands + float64 fix-up) must give the oracle's
     float64 signatures with either operand encoding — BF16 x 2 (default) and TF32 x 2; the bare
-    tensor-core signs may only differ where |x.w| is below the stated tolerance
-    (c + dims / 4) * 2^-22 * |x| * max|w|, c = 52 (BF16) / 8 (TF32)."""
+    tensor-core signs may only differ where |x.w| is below
+    (c + dims / 4) * 2^-22 * |x| * max|w|, c = 52 (BF16) / 8 (TF32) — the TF32 kernel's tolerance and an upper
+    bound of the BF16 kernel's (which uses prefix norms for the accumulation term, project_tc.cu)."""
     import torch
     import np_sims.lsh as lsh
     from np_sims import _lib
