@@ -383,6 +383,47 @@ def test_tensor_core_hash_equals_float64_oracle(nps, n, dims, bits):
               f"|x.w| = {used:.3f} of the tolerance), recomputed in float64 {frac:.3%}")
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("structure", ["iid", "decaying", "front_loaded", "sparse_w"])
+def test_bf16_hash_tolerance_is_the_documented_one(nps, structure):
+    """The BF16 kernel trusts an accumulator when |C1 + C2| >= (52 + 0.006 D) 2^-22 |x| max|w| + 2.625 * 1.02 * 2^-22 * P,
+    P = sum_i |x[0 : 16 (i+1))| max_j |w_j[0 : 16 (i+1))| (project_tc.cu).  Actual tensor-core errors are ~1000 x smaller
+    than that, so a kernel whose tolerance came out too SMALL would still hash correctly in every other test: here
+    the number of pairs it recomputes in float64 is compared with the number the documented formula selects (NumPy,
+    float64), on rows and projections with and without structure along the dimension axis."""
+    import np_sims.lsh as lsh
+    n, dims, bits = 4096, 768, 1024
+    rng = np.random.default_rng(11)
+    X = rng.standard_normal((n, dims)).astype(np.float32)
+    np.random.seed(5)
+    W = np.asarray(lsh.create_projections(bits, dims)).copy()
+    if structure == "decaying":
+        X *= np.exp(-np.arange(dims) / 100.0).astype(np.float32)
+    elif structure == "front_loaded":
+        X[:, :16] *= 50.0
+        X[:, 400:] = 0.0
+    elif structure == "sparse_w":
+        W[:, rng.permutation(dims)[: dims // 2]] = 0.0
+        W *= rng.uniform(0.5, 2.0, size=(bits, 1))
+    want = oracle.index_np(X, W)
+    got = np.asarray(lsh.index(X, W))
+    st = lsh.hash_stats()
+    assert st["path"] == "tc-split+fixup" and not st["overflowed"]
+    assert np.array_equal(got, want)
+    x64, nblk = X.astype(np.float64), dims // 16
+    dots = x64 @ W.T
+    px = np.sqrt(np.cumsum((x64 ** 2).reshape(n, nblk, 16).sum(axis=2), axis=1))                  # [n, nblk]
+    qtab = np.sqrt(np.cumsum((W ** 2).reshape(bits, nblk, 16).sum(axis=2), axis=1)).max(axis=0)   # [nblk]
+    wmax = np.linalg.norm(W, axis=1).max()
+    tol = ((52 + 0.006 * dims) * 2.0 ** -22 * np.linalg.norm(x64, axis=1) * wmax + 2.625 * 1.02 * 2.0 ** -22 * (px @ qtab))
+    lo = np.count_nonzero(np.abs(dots) < tol[:, None] * 0.995)
+    hi = np.count_nonzero(np.abs(dots) < tol[:, None] * 1.005)
+    assert lo <= st["recomputed"] <= hi, (structure, lo, st["recomputed"], hi)
+    full = np.count_nonzero(np.abs(dots) < ((52 + dims / 4) * 2.0 ** -22 * np.linalg.norm(x64, axis=1) * wmax)[:, None])
+    print(f"K1T bf16 {structure}: {st['recomputed']} pairs recomputed ({st['recomputed'] / dots.size:.3%}); "
+          f"the full-norm (52 + D/4) tolerance of round 1 would have selected {full}")
+
+
 def test_tensor_core_hash_degenerate_inputs(nps):
     import np_sims.lsh as lsh
     np.random.seed(1)
