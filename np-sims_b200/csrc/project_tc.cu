@@ -155,24 +155,33 @@ __device__ __forceinline__ void project_epilogue(const ProjTcParams& p, uint32_t
             if (acc_s != nullptr)
                 tol = fmaf(p.acc_scale, reinterpret_cast<const volatile float*>(acc_s)[(t_idx % kPtNormBufs) * kPtTileRows + r_in_tile], tol);
             const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + buf * (2u * NT);
+            // Between acc_full and the release below the next item's MMAs wait (the BF16 kernel's accumulator is single-
+            // buffered): three instructions per value here — the add, a funnel shift that collects the sign bit, a
+            // running minimum of |a| — and the per-value tolerance test only for the 16-column groups whose minimum is
+            // below the tolerance (a = -0.0 has the sign bit set but is below every tolerance, so it is recomputed).
             uint32_t sign_m[G], unsure_m[G];
 #pragma unroll
             for (uint32_t g = 0; g < G; ++g) {
-                uint32_t bits = 0, unsure = 0;      // per column: sign, |acc| below the tolerance
+                uint32_t neg = 0, unsure = 0;      // neg: sign bits, first column in bit 31
 #pragma unroll
                 for (uint32_t h = 0; h < 2; ++h) {  // 16 columns at a time: 32 live registers, not 64
                     uint32_t v1[16], v2[16];
                     tmem_ld16_at<0>(t_addr + g * 32u + h * 16u, v1);
                     tmem_ld16_at<0>(t_addr + NT + g * 32u + h * 16u, v2);
                     tmem_ld_wait();
+                    float a[16], lowest = __int_as_float(0x7f800000);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float a = __uint_as_float(v1[j]) + __uint_as_float(v2[j]);
-                        bits |= (a >= 0.f ? 1u : 0u) << (h * 16u + j);
-                        unsure |= (fabsf(a) < tol ? 1u : 0u) << (h * 16u + j);
+                        a[j] = __uint_as_float(v1[j]) + __uint_as_float(v2[j]);
+                        neg = __funnelshift_l(__float_as_uint(a[j]), neg, 1);
+                        lowest = fminf(lowest, fabsf(a[j]));
+                    }
+                    if (!(lowest >= tol)) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) unsure |= (fabsf(a[j]) < tol ? 1u : 0u) << (h * 16u + j);
                     }
                 }
-                sign_m[g] = bits;
+                sign_m[g] = ~__brev(neg);           // bit j = (a_j >= 0) wherever the accumulator is trusted
                 unsure_m[g] = !valid ? 0u : (tame ? unsure : 0xFFFFFFFFu);
             }
             tc_fence_before();
